@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- gs_op(add,double) throughput on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one gs(add,double) over one rank-local field of the synthetic
+Nek5000-style mesh: at N=1 the M7 box 64x64x48, order 7
+(100 663 296 DOF); at N>1 the same box per GPU as z-slabs of a 64x64x(48N)
+mesh (weak scaling, pairwise halo exchange over NCCL).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput,
+`e2e` the same call made with pinned HOST buffers through the public gs()
+(H2D + kernels + D2H inside the timed region), `roofline` the fused kernel's
+algorithmic bytes / CUDA-event time against the measured HBM peak, and
+`cpu_baseline` the CPU oracle timed on this box's host cores on a bounded
+sample.  --impl reference times the reference's CPU algorithm only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "exaflow-exags-upc_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+
+EX, EY, EZ, ORDER = 64, 64, 48, 7          # M7 per GPU
+METRIC = "gs_op(add,double) throughput"
+UNIT = "GDOF/s"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6
+                          for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+#  CPU arm: the oracle (port of the reference algorithm) on the host cores
+# --------------------------------------------------------------------------
+def cpu_arm(steps: int, warmup: int, seconds_budget: float = 25.0) -> dict:
+    """Times the reference CPU algorithm on a bounded sample of the workload:
+    a 64x64xEZs slab stack of the same N=7 mesh, one z-slab per emulated rank
+    (the reference's SPMD threads), ranks run on separate host cores."""
+    import oracle as O
+    from exags_b200 import semmesh
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ranks = max(1, min(cores, 16))
+    ez_per = 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(ranks))
+    ids = [semmesh.box_ids(EX, EY, ez_per, ORDER, ez0=r * ez_per, Ez_global=ez_per * ranks)
+           for r in range(ranks)]
+    n_total = sum(a.size for a in ids)
+    orc = O.Oracle(ids, method=O.METHOD_PAIRWISE)
+    us = [semmesh.field_values(semmesh.slab_dof_numbers(EX, EY, ez_per, ORDER, r * ez_per), np.float64)
+          for r in range(ranks)]
+    for _ in range(max(1, warmup)):
+        orc.exec(us, O.M_PLAIN, 1, O.D_DOUBLE, O.O_ADD, 0)
+    t_all, done = 0.0, 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.exec(us, O.M_PLAIN, 1, O.D_DOUBLE, O.O_ADD, 0)
+        t_all += time.perf_counter() - t0
+        done += 1
+        if t_all > seconds_budget:
+            break
+    ms = 1e3 * t_all / done
+    return {"value": n_total / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": ranks, "kind": "port",
+            "sample": f"{EX}x{EY}x{ez_per * ranks} el N={ORDER} ({n_total} DOF) as {ranks} z-slab ranks, "
+                      f"pairwise, {done} steps", "ms_per_step": ms, "steps": done}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"M7 {EX}x{EY}x{EZ} hex N={ORDER} per GPU, gs(add,double); "
+                                   "each step a bounded sample: " + cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+#  GPU arm
+# --------------------------------------------------------------------------
+def run_gpu(args) -> None:
+    import torch
+    import exags_b200 as X
+    from exags_b200 import semmesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    X.lib().exags_set_device(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- mesh + setup ------------------------------------------------
+    t0 = time.perf_counter()
+    ids = semmesh.box_ids(EX, EY, EZ, ORDER, ez0=rank * EZ, Ez_global=EZ * world)
+    n = ids.size
+    t1 = time.perf_counter()
+    g = X.gs_setup(ids, method=X.gs_pairwise, verbose=0)
+    t_setup = time.perf_counter() - t1
+    info = g.info()
+    del ids
+    dof = semmesh.slab_dof_numbers(EX, EY, EZ, ORDER, rank * EZ)
+    host = torch.from_numpy(semmesh.field_values(dof, np.float64)).pin_memory()
+    del dof
+    u = host.cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        X.gs_async(u, X.mode_plain, 1, X.gs_double, X.gs_add, 0, g, stream)
+
+    # ---- device-resident throughput ------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = X.kernel_launches()
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    launches = X.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the public blocking gs() on host memory ----
+    e2e_steps = max(1, min(args.steps, 5))
+    hbuf = host.clone().pin_memory()
+    X.gs(hbuf.numpy(), X.gs_double, X.gs_add, 0, g)          # warm-up (allocates staging)
+    hbuf.copy_(host)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        X.gs(hbuf.numpy(), X.gs_double, X.gs_add, 0, g)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - w0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": n * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+           "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "gs(u_host, gs_double, gs_add, 0, gsh, NULL) on pinned host memory"}
+
+    # ---- roofline of the dominant kernel (the fused interior kernel) ----
+    peak, peak_src = hbm_peak()
+    G, S, nsec = info["groups"], info["members"], info["sectors_f64"]
+    b_alg = 2 * 32 * nsec + 4 * S + 4 * (G + 1)
+    kern_ms = sum(per) / len(per)
+    achieved = b_alg / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes": b_alg, "kernel": "k_fused<double,add,plain>",
+                "kernel_ms_mean": kern_ms, "kernel_ms_min": per[0], "kernel_ms_median": per[len(per) // 2],
+                "frac_vs_8TBps": achieved / 8000.0}
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu:
+            cb = cpu_arm(10, 2, seconds_budget=20.0)
+            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"M7 {EX}x{EY}x{EZ} hex N={ORDER} per GPU "
+                                       f"({n} DOF/GPU, G={G}, S={S}), gs(add,double), "
+                                       + ("1 rank" if world == 1 else f"z-slabs of {EX}x{EY}x{EZ * world}, pairwise halo over NCCL"),
+                           "l2": "field (805 MB/GPU) is larger than the 126 MB L2; no flush needed",
+                           "setup_s": t_setup, "method": "pairwise"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    X.gs_free(g)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

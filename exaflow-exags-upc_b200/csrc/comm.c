@@ -1,0 +1,596 @@
+/* comm.c -- communicator, rank identity, host rendezvous and NCCL bootstrap.
+ *
+ * Replaces the reference's UPC "comm" layer (src/comm.h:128-206,
+ * src/comm.upc:35-424,706-959) for the gs hot path.  The reference keeps
+ * rank identity in MYTHREAD/THREADS and moves data with upc_memput + polled
+ * flags in shared directories.  Here:
+ *
+ *   - rank identity comes from the launcher environment (one process per
+ *     GPU: RANK/WORLD_SIZE/LOCAL_RANK as torchrun sets them);
+ *   - host-side setup traffic (the id rendezvous of gs_setup, comm_scan,
+ *     comm_allreduce on host vectors) goes through a POSIX shared-memory
+ *     rendezvous on the node -- the direct analogue of the PGAS segment,
+ *     and it works without a GPU, which is how the multi-rank host logic is
+ *     tested;
+ *   - per-call halo traffic goes through NCCL send/recv over NVLink on a
+ *     dedicated high-priority stream (gs_host.c); NCCL is dlopen()ed on first
+ *     multi-rank use so single-GPU users never need it.
+ *
+ * One node only (the north star is one 8xB200 box).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+#include <float.h>
+#include <limits.h>
+#include "exags_internal.h"
+
+#define XW_MAXNP   64
+#define XW_SMALL   4096            /* per-rank inline area for small collectives */
+#define XW_MAGIC   0x45584147u     /* "EXAG" */
+
+struct xw_ctl {
+  _Atomic unsigned magic;
+  unsigned np;
+  _Atomic unsigned attached;
+  _Atomic unsigned bar_count;
+  _Atomic unsigned bar_sense;
+  unsigned long long pub_bytes[XW_MAXNP];
+  char small[XW_MAXNP][XW_SMALL];
+};
+
+struct xg_world {
+  int rank, np, local_rank, device, has_cuda;
+  /* host rendezvous */
+  char key[64];
+  struct xw_ctl *ctl;
+  unsigned sense;
+  unsigned long long epoch;
+  /* device side */
+  void *stream[2];
+  void *event[4];
+  void *scratch[3];
+  size_t scratch_bytes[3];
+  /* nccl */
+  void *nccl_lib;
+  void *nccl_comm;
+};
+
+static struct xg_world *g_world = 0;
+static int g_device_override = -1;
+comm_ptr exags_glb_comm = 0;
+
+static const char *env_first(const char *const *names)
+{
+  for (; *names; ++names) {
+    const char *v = getenv(*names);
+    if (v && *v) return v;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/*  host rendezvous                                                    */
+/* ------------------------------------------------------------------ */
+static void relax(unsigned *spins)
+{
+  if (++*spins < 200) { __asm__ __volatile__("pause"); return; }
+  if (*spins < 2000) { sched_yield(); return; }
+  struct timespec ts = { 0, 50000 };
+  nanosleep(&ts, 0);
+}
+
+static void make_key(struct xg_world *w)
+{
+  const char *k = getenv("EXAGS_JOB_KEY");
+  if (k && *k) { snprintf(w->key, sizeof w->key, "%.48s", k); return; }
+  /* every rank of one launch has the same parent (torchrun agent, mpirun,
+     a test harness): key on that parent's pid and start time */
+  unsigned long long start = 0;
+  char path[64], line[1024];
+  snprintf(path, sizeof path, "/proc/%d/stat", (int)getppid());
+  FILE *f = fopen(path, "r");
+  if (f) {
+    if (fgets(line, sizeof line, f)) {
+      char *p = strrchr(line, ')');
+      int field = 2;
+      while (p && *p && field < 22) { if (*p == ' ') ++field; ++p; }
+      if (p) start = strtoull(p, 0, 10);
+    }
+    fclose(f);
+  }
+  const char *port = getenv("MASTER_PORT");
+  snprintf(w->key, sizeof w->key, "%d-%llu-%s", (int)getppid(), start, port ? port : "0");
+}
+
+static void ctl_name(const struct xg_world *w, char *out, size_t cap)
+{ snprintf(out, cap, "/exags-%s-ctl", w->key); }
+static void pub_name(const struct xg_world *w, int rank, unsigned long long epoch, char *out, size_t cap)
+{ snprintf(out, cap, "/exags-%s-r%d-e%llu", w->key, rank, epoch); }
+
+static void rendezvous_attach(struct xg_world *w)
+{
+  char name[128];
+  make_key(w);
+  ctl_name(w, name, sizeof name);
+  int fd = -1;
+  if (w->rank == 0) {
+    shm_unlink(name);
+    fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) xfail("comm: cannot create rendezvous segment %s: %s", name, strerror(errno));
+    if (ftruncate(fd, (off_t)sizeof(struct xw_ctl)) != 0)
+      xfail("comm: cannot size rendezvous segment: %s", strerror(errno));
+  } else {
+    unsigned spins = 0; double waited = 0;
+    for (;;) {
+      fd = shm_open(name, O_RDWR, 0600);
+      if (fd >= 0) {
+        struct stat st;
+        if (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(struct xw_ctl)) break;
+        close(fd); fd = -1;
+      }
+      relax(&spins);
+      if (spins >= 2000) waited += 50e-6;
+      if (waited > 120.0) xfail("comm: rank %d timed out waiting for rank 0's rendezvous segment %s", w->rank, name);
+    }
+  }
+  w->ctl = (struct xw_ctl *)mmap(0, sizeof(struct xw_ctl), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (w->ctl == MAP_FAILED) xfail("comm: mmap of rendezvous segment failed: %s", strerror(errno));
+  if (w->rank == 0) {
+    w->ctl->np = (unsigned)w->np;
+    atomic_store(&w->ctl->attached, 1u);
+    atomic_store(&w->ctl->bar_count, 0u);
+    atomic_store(&w->ctl->bar_sense, 0u);
+    atomic_store(&w->ctl->magic, XW_MAGIC);
+  } else {
+    unsigned spins = 0;
+    while (atomic_load(&w->ctl->magic) != XW_MAGIC) relax(&spins);
+    if (w->ctl->np != (unsigned)w->np)
+      xfail("comm: rendezvous segment is for %u ranks, this job has %d", w->ctl->np, w->np);
+    atomic_fetch_add(&w->ctl->attached, 1u);
+  }
+  unsigned spins = 0;
+  while (atomic_load(&w->ctl->attached) < (unsigned)w->np) relax(&spins);
+  w->sense = 0;
+}
+
+void xg_host_barrier(struct xg_world *w)
+{
+  if (w->np == 1) return;
+  unsigned mine = (w->sense ^= 1u);
+  if (atomic_fetch_add(&w->ctl->bar_count, 1u) == (unsigned)w->np - 1u) {
+    atomic_store(&w->ctl->bar_count, 0u);
+    atomic_store(&w->ctl->bar_sense, mine);
+  } else {
+    unsigned spins = 0;
+    while (atomic_load(&w->ctl->bar_sense) != mine) relax(&spins);
+  }
+}
+
+/* publish a block of bytes for this epoch; returns a writable mapping */
+static void *pub_create(struct xg_world *w, size_t bytes)
+{
+  char name[128];
+  pub_name(w, w->rank, w->epoch, name, sizeof name);
+  shm_unlink(name);
+  int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) xfail("comm: cannot create exchange segment %s: %s", name, strerror(errno));
+  size_t sz = bytes ? bytes : 1;
+  if (ftruncate(fd, (off_t)sz) != 0) xfail("comm: cannot size exchange segment (%lu bytes): %s", (unsigned long)sz, strerror(errno));
+  void *p = mmap(0, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) xfail("comm: mmap of exchange segment failed: %s", strerror(errno));
+  w->ctl->pub_bytes[w->rank] = bytes;
+  return p;
+}
+
+static const void *pub_peer(struct xg_world *w, int peer, size_t *bytes)
+{
+  char name[128];
+  pub_name(w, peer, w->epoch, name, sizeof name);
+  int fd = shm_open(name, O_RDONLY, 0600);
+  if (fd < 0) xfail("comm: cannot open exchange segment %s: %s", name, strerror(errno));
+  size_t sz = (size_t)w->ctl->pub_bytes[peer];
+  void *p = mmap(0, sz ? sz : 1, PROT_READ, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) xfail("comm: mmap of peer exchange segment failed: %s", strerror(errno));
+  *bytes = sz;
+  return p;
+}
+
+static void pub_destroy(struct xg_world *w, void *mine, size_t bytes)
+{
+  char name[128];
+  munmap(mine, bytes ? bytes : 1);
+  pub_name(w, w->rank, w->epoch, name, sizeof name);
+  shm_unlink(name);
+  ++w->epoch;
+}
+
+void xg_host_allgather(struct xg_world *w, const void *in, size_t bytes, void *out)
+{
+  if (w->np == 1) { memcpy(out, in, bytes); return; }
+  if (bytes <= XW_SMALL) {
+    memcpy(w->ctl->small[w->rank], in, bytes);
+    xg_host_barrier(w);
+    for (int p = 0; p < w->np; ++p) memcpy((char *)out + (size_t)p * bytes, w->ctl->small[p], bytes);
+    xg_host_barrier(w);
+    return;
+  }
+  void *mine = pub_create(w, bytes);
+  memcpy(mine, in, bytes);
+  xg_host_barrier(w);
+  for (int p = 0; p < w->np; ++p) {
+    size_t pb;
+    const void *q = pub_peer(w, p, &pb);
+    memcpy((char *)out + (size_t)p * bytes, q, bytes);
+    munmap((void *)q, pb ? pb : 1);
+  }
+  xg_host_barrier(w);
+  pub_destroy(w, mine, bytes);
+}
+
+void *xg_host_alltoallv(struct xg_world *w, const void *rows, size_t rowbytes,
+                        const size_t *sendcnt, size_t *recvcnt, size_t *nrecv)
+{
+  int np = w->np;
+  size_t total = 0;
+  for (int p = 0; p < np; ++p) total += sendcnt[p];
+  if (np == 1) {
+    void *out = xmalloc_(total * rowbytes, __FILE__, __LINE__);
+    memcpy(out, rows, total * rowbytes);
+    recvcnt[0] = total; *nrecv = total;
+    return out;
+  }
+  unsigned long long *mine_cnt = xnew(unsigned long long, np);
+  unsigned long long *all_cnt = xnew(unsigned long long, (size_t)np * np);
+  for (int p = 0; p < np; ++p) mine_cnt[p] = sendcnt[p];
+  xg_host_allgather(w, mine_cnt, (size_t)np * sizeof *mine_cnt, all_cnt);
+  size_t got = 0;
+  for (int p = 0; p < np; ++p) { recvcnt[p] = (size_t)all_cnt[(size_t)p * np + w->rank]; got += recvcnt[p]; }
+  void *mine = pub_create(w, total * rowbytes);
+  memcpy(mine, rows, total * rowbytes);
+  xg_host_barrier(w);
+  char *out = (char *)xmalloc_(got * rowbytes, __FILE__, __LINE__);
+  size_t o = 0;
+  for (int p = 0; p < np; ++p) {
+    size_t skip = 0, pb;
+    for (int q = 0; q < w->rank; ++q) skip += (size_t)all_cnt[(size_t)p * np + q];
+    if (!recvcnt[p]) continue;
+    const char *src = (const char *)pub_peer(w, p, &pb);
+    memcpy(out + o * rowbytes, src + skip * rowbytes, recvcnt[p] * rowbytes);
+    munmap((void *)src, pb ? pb : 1);
+    o += recvcnt[p];
+  }
+  xg_host_barrier(w);
+  pub_destroy(w, mine, total * rowbytes);
+  free(mine_cnt); free(all_cnt);
+  *nrecv = got;
+  return out;
+}
+
+/* ------------------------------------------------------------------ */
+/*  NCCL via dlopen                                                    */
+/* ------------------------------------------------------------------ */
+typedef struct { char internal[128]; } xg_nccl_uid;
+static struct {
+  int (*GetUniqueId)(xg_nccl_uid *);
+  int (*CommInitRank)(void **, int, xg_nccl_uid, int);
+  int (*CommDestroy)(void *);
+  int (*Send)(const void *, size_t, int, int, void *, void *);
+  int (*Recv)(void *, size_t, int, int, void *, void *);
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, void *);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
+  const char *(*GetErrorString)(int);
+} nc;
+
+#define NC(call)                                                              \
+  do {                                                                        \
+    int r_ = (call);                                                          \
+    if (r_ != 0)                                                              \
+      xfail("NCCL error: %s (%s)", nc.GetErrorString ? nc.GetErrorString(r_) : "?", #call); \
+  } while (0)
+
+static void nccl_load(struct xg_world *w)
+{
+  if (w->nccl_lib) return;
+  const char *names[] = { getenv("EXAGS_NCCL_LIB"), "libnccl.so.2", "libnccl.so", 0 };
+  for (int i = 0; i < 3 && !w->nccl_lib; ++i)
+    if (names[i] && *names[i]) w->nccl_lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!w->nccl_lib) xfail("comm: np=%d needs NCCL but libnccl.so.2 could not be loaded: %s", w->np, dlerror());
+#define SYM(field, name)                                                      \
+  do {                                                                        \
+    *(void **)(&nc.field) = dlsym(w->nccl_lib, name);                         \
+    if (!nc.field) xfail("comm: %s missing from NCCL library", name);         \
+  } while (0)
+  SYM(GetErrorString, "ncclGetErrorString");
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+#undef SYM
+}
+
+void *xg_world_nccl(struct xg_world *w)
+{
+  if (w->nccl_comm || w->np == 1) return w->nccl_comm;
+  if (!w->has_cuda) xfail("comm: NCCL requested without a CUDA device");
+  nccl_load(w);
+  xg_nccl_uid uid, *all = xnew(xg_nccl_uid, w->np);
+  memset(&uid, 0, sizeof uid);
+  if (w->rank == 0) NC(nc.GetUniqueId(&uid));
+  xg_host_allgather(w, &uid, sizeof uid, all);
+  NC(nc.CommInitRank(&w->nccl_comm, w->np, all[0], w->rank));
+  free(all);
+  return w->nccl_comm;
+}
+
+/* nccl dtype / op codes (nccl.h: ncclInt32=2, ncclInt64=4, ncclFloat32=7,
+   ncclFloat64=8; ncclSum=0, ncclProd=1, ncclMax=2, ncclMin=3) */
+static int nccl_dtype(int xd)
+{
+  static const int t[4] = { 8, 7, 2, 4 };
+  return t[xd];
+}
+static int nccl_op(int xop)
+{
+  switch (xop) {
+    case XO_ADD: return 0;
+    case XO_MUL: return 1;
+    case XO_MAX: return 2;
+    case XO_MIN: return 3;
+  }
+  xfail("gs: op %d has no NCCL reduction", xop);
+  return 0;
+}
+
+void xg_nccl_group_start(struct xg_world *w) { (void)w; NC(nc.GroupStart()); }
+void xg_nccl_group_end(struct xg_world *w)   { (void)w; NC(nc.GroupEnd()); }
+void xg_nccl_send(struct xg_world *w, const void *buf, size_t count, int xd, int peer, void *stream)
+{ NC(nc.Send(buf, count, nccl_dtype(xd), peer, xg_world_nccl(w), stream)); }
+void xg_nccl_recv(struct xg_world *w, void *buf, size_t count, int xd, int peer, void *stream)
+{ NC(nc.Recv(buf, count, nccl_dtype(xd), peer, xg_world_nccl(w), stream)); }
+void xg_nccl_allreduce(struct xg_world *w, void *buf, size_t count, int xd, int xop, void *stream)
+{ NC(nc.AllReduce(buf, buf, count, nccl_dtype(xd), nccl_op(xop), xg_world_nccl(w), stream)); }
+
+/* ------------------------------------------------------------------ */
+/*  world                                                              */
+/* ------------------------------------------------------------------ */
+static void world_atexit(void)
+{
+  struct xg_world *w = g_world;
+  if (!w) return;
+  if (w->np > 1 && w->ctl && w->rank == 0) {
+    char name[128];
+    ctl_name(w, name, sizeof name);
+    shm_unlink(name);
+  }
+}
+
+struct xg_world *xg_world_get(void)
+{
+  if (g_world) return g_world;
+  struct xg_world *w = xnew0(struct xg_world, 1);
+  static const char *const rk[] = { "EXAGS_RANK", "RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", 0 };
+  static const char *const sz[] = { "EXAGS_NP", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", 0 };
+  static const char *const lr[] = { "EXAGS_LOCAL_RANK", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", 0 };
+  const char *v;
+  w->rank = (v = env_first(rk)) ? atoi(v) : 0;
+  w->np = (v = env_first(sz)) ? atoi(v) : 1;
+  w->local_rank = (v = env_first(lr)) ? atoi(v) : w->rank;
+  if (w->np < 1 || w->rank < 0 || w->rank >= w->np || w->np > XW_MAXNP)
+    xfail("comm: bad rank/size %d/%d from the environment (max %d ranks)", w->rank, w->np, XW_MAXNP);
+  exags_comm_gbl_id = (exags_uint)w->rank;
+  exags_comm_gbl_np = (exags_uint)w->np;
+
+  const char *host_only = getenv("EXAGS_HOST_SETUP_ONLY");
+  int ndev = (host_only && atoi(host_only)) ? 0 : xcu_device_count();
+  w->has_cuda = ndev > 0;
+  w->device = -1;
+  if (w->has_cuda) {
+    w->device = g_device_override >= 0 ? g_device_override : w->local_rank % ndev;
+    xcu_set_device(w->device);
+    w->stream[0] = xcu_stream_create(0);
+    w->stream[1] = xcu_stream_create(1);
+    for (int i = 0; i < 4; ++i) w->event[i] = xcu_event_create();
+  }
+  if (w->np > 1) rendezvous_attach(w);
+  g_world = w;
+  atexit(world_atexit);
+  return w;
+}
+
+int xg_world_rank(const struct xg_world *w) { return w->rank; }
+int xg_world_np(const struct xg_world *w) { return w->np; }
+int xg_world_has_cuda(const struct xg_world *w) { return w->has_cuda; }
+void *xg_world_stream(struct xg_world *w, int which) { return w->stream[which]; }
+void *xg_world_event(struct xg_world *w, int which) { return w->event[which]; }
+
+void *xg_world_scratch(struct xg_world *w, int which, size_t bytes)
+{
+  if (w->scratch_bytes[which] < bytes) {
+    if (w->scratch[which]) { xcu_device_sync(); xcu_free(w->scratch[which]); }
+    size_t want = bytes + bytes / 4 + 256;
+    w->scratch[which] = xcu_malloc(want);
+    w->scratch_bytes[which] = want;
+  }
+  return w->scratch[which];
+}
+
+void exags_set_device(int device) { g_device_override = device; }
+int exags_get_device(void) { return g_world ? g_world->device : g_device_override; }
+
+/* ------------------------------------------------------------------ */
+/*  public communicator API                                            */
+/* ------------------------------------------------------------------ */
+void exags_comm_world(comm_ptr *cpp)
+{
+  if (!cpp) return;
+  struct xg_world *w = xg_world_get();
+  comm_ptr cp = xnew0(struct comm, 1);
+  cp->h = 0;
+  cp->id = w->rank;
+  cp->np = w->np;
+  cp->priv = w;
+  cp->ref_count = xnew0(int, 1);
+  *cpp = cp;
+}
+
+void exags_comm_init(void)
+{
+  if (!exags_glb_comm) exags_comm_world(&exags_glb_comm);
+}
+
+void exags_comm_finalize(void) {}
+
+void exags_comm_dup(comm_ptr *cpp, const comm_ptr cp)
+{
+  if (!cpp || !cp) return;
+  comm_ptr d = xnew(struct comm, 1);
+  *d = *cp;
+  ++*d->ref_count;
+  *cpp = d;
+}
+
+void exags_comm_free(comm_ptr *cpp)
+{
+  if (!cpp || !*cpp) return;
+  comm_ptr cp = *cpp;
+  if (*cp->ref_count == 0) free(cp->ref_count);
+  else --*cp->ref_count;
+  free(cp);
+  *cpp = 0;
+}
+
+void exags_comm_np(const comm_ptr cp, int *np) { if (cp && np) *np = cp->np; }
+void exags_comm_id(const comm_ptr cp, int *id) { if (cp && id) *id = cp->id; }
+
+void exags_comm_time(double *tm)
+{
+  if (!tm) return;
+  struct timeval tv;
+  gettimeofday(&tv, 0);
+  *tm = (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+}
+
+void exags_comm_barrier(const comm_ptr cp)
+{
+  if (!cp) return;
+  xg_host_barrier((struct xg_world *)cp->priv);
+}
+
+void exags_comm_bcast(const comm_ptr cp, void *p, size_t n, exags_uint root)
+{
+  if (!cp || !p || cp->np == 1) return;
+  struct xg_world *w = (struct xg_world *)cp->priv;
+  char *all = (char *)xmalloc_(n * (size_t)cp->np, __FILE__, __LINE__);
+  xg_host_allgather(w, p, n, all);
+  memcpy(p, all + (size_t)root * n, n);
+  free(all);
+}
+
+/* host-side element-wise reductions, rank order 0..np-1 on every rank so all
+   ranks get bit-identical results */
+#define HOST_COMBINE(T, OPC)                                                  \
+  do {                                                                        \
+    T *a_ = (T *)acc; const T *b_ = (const T *)in;                            \
+    for (size_t k_ = 0; k_ < n; ++k_) { T x = a_[k_], y = b_[k_]; OPC; a_[k_] = x; } \
+  } while (0)
+
+static void host_combine(void *acc, const void *in, size_t n, int xd, int xop)
+{
+#define BY_OP(T)                                                              \
+  switch (xop) {                                                              \
+    case XO_ADD: HOST_COMBINE(T, x += y); break;                              \
+    case XO_MUL: HOST_COMBINE(T, x *= y); break;                              \
+    case XO_MIN: HOST_COMBINE(T, if (y < x) x = y); break;                    \
+    case XO_MAX: HOST_COMBINE(T, if (y > x) x = y); break;                    \
+    default: xfail("comm: op %d not supported in host reductions", xop);      \
+  }
+  switch (xd) {
+    case XD_F64: BY_OP(double); break;
+    case XD_F32: BY_OP(float); break;
+    case XD_I32: BY_OP(int); break;
+    case XD_I64: BY_OP(long long); break;
+    default: xfail("comm: bad domain %d", xd);
+  }
+#undef BY_OP
+}
+
+static void host_identity(void *out, size_t n, int xd, int xop)
+{
+#define FILL(T, lo, hi)                                                       \
+  do {                                                                        \
+    T e = xop == XO_MUL ? (T)1 : xop == XO_MIN ? (T)(hi) : xop == XO_MAX ? (T)(lo) : (T)0; \
+    for (size_t k_ = 0; k_ < n; ++k_) ((T *)out)[k_] = e;                     \
+  } while (0)
+  switch (xd) {
+    case XD_F64: FILL(double, -DBL_MAX, DBL_MAX); break;
+    case XD_F32: FILL(float, -FLT_MAX, FLT_MAX); break;
+    case XD_I32: FILL(int, INT_MIN, INT_MAX); break;
+    case XD_I64: FILL(long long, LLONG_MIN, LLONG_MAX); break;
+    default: xfail("comm: bad domain %d", xd);
+  }
+#undef FILL
+}
+
+void exags_comm_allreduce(const comm_ptr cp, gs_dom dom, gs_op_t op, void *v, exags_uint vn, void *buf)
+{
+  (void)buf;
+  if (!cp || !vn || cp->np == 1) return;
+  int xd = xg_dom_of((int)dom);
+  if (xd < 0) xfail("comm_allreduce: bad domain %d", (int)dom);
+  struct xg_world *w = (struct xg_world *)cp->priv;
+  size_t bytes = (size_t)vn * xg_dom_bytes(xd);
+  char *all = (char *)xmalloc_(bytes * (size_t)cp->np, __FILE__, __LINE__);
+  xg_host_allgather(w, v, bytes, all);
+  memcpy(v, all, bytes);
+  for (int p = 1; p < cp->np; ++p) host_combine(v, all + (size_t)p * bytes, vn, xd, (int)op);
+  free(all);
+}
+
+void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
+                     const void *v, exags_uint vn, void *buffer)
+{
+  (void)buffer;
+  if (!cp || !vn) return;
+  int xd = xg_dom_of((int)dom);
+  if (xd < 0) xfail("comm_scan: bad domain %d", (int)dom);
+  struct xg_world *w = (struct xg_world *)cp->priv;
+  size_t bytes = (size_t)vn * xg_dom_bytes(xd);
+  char *all = (char *)xmalloc_(bytes * (size_t)cp->np, __FILE__, __LINE__);
+  xg_host_allgather(w, v, bytes, all);
+  char *excl = (char *)scan, *tot = (char *)scan + bytes;
+  host_identity(excl, vn, xd, (int)op);
+  host_identity(tot, vn, xd, (int)op);
+  for (int p = 0; p < cp->np; ++p) {
+    if (p < cp->id) host_combine(excl, all + (size_t)p * bytes, vn, xd, (int)op);
+    host_combine(tot, all + (size_t)p * bytes, vn, xd, (int)op);
+  }
+  free(all);
+}
+
+double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n)
+{
+  double s = 0, b;
+  for (exags_uint i = 0; i < n; ++i) s += v[i] * w[i];
+  exags_comm_allreduce(cp, gs_double, gs_add, &s, 1, &b);
+  return s;
+}

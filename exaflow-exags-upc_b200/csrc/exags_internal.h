@@ -1,0 +1,182 @@
+/* exags_internal.h -- private declarations shared by the host C code and the
+ * CUDA translation unit.  Nothing in here is ABI. */
+#ifndef EXAGS_INTERNAL_H
+#define EXAGS_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#define EXAGS_NO_INT_MACROS 1
+#define EXAGS_FORTRAN_GS_OP 1   /* keep the name gs_op free for the Fortran entry point */
+#include "../../include/exags.h"
+#include "../../include/exags_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t  i64;
+
+#define XG_NONE ((u32)0xFFFFFFFFu)   /* the reference's (uint)-1 sentinel */
+#define XG_MAXV 8                    /* component pointers passed per launch */
+
+/* internal storage type of a gs_dom value; both ABI flavours map onto it
+   (gs_long and gs_long_long are both 64-bit on LP64, src/gs_defs.h:18-23) */
+enum { XD_F64 = 0, XD_F32 = 1, XD_I32 = 2, XD_I64 = 3, XD_N = 4 };
+enum { XO_ADD = 0, XO_MUL = 1, XO_MIN = 2, XO_MAX = 3, XO_BPR = 4, XO_N = 5 };
+enum { XM_PLAIN = 0, XM_VEC = 1, XM_MANY = 2 };
+
+static inline int xg_dom_of(int dom)      /* ABI dom -> storage type, -1 bad */
+{
+  static const int t[5] = { XD_F64, XD_F32, XD_I32, XD_I64, XD_I64 };
+  return (dom >= 0 && dom < 5) ? t[dom] : -1;
+}
+static inline unsigned xg_dom_bytes(int xd)
+{
+  static const unsigned s[4] = { 8, 4, 4, 8 };
+  return s[xd];
+}
+
+#define xfail(...) exags_fail(1, __FILE__, __LINE__, __VA_ARGS__)
+
+/* ---- memory ------------------------------------------------------------ */
+void *xmalloc_(size_t bytes, const char *file, unsigned line);
+void *xcalloc_(size_t bytes, const char *file, unsigned line);
+void *xrealloc_(void *p, size_t bytes, const char *file, unsigned line);
+#define xnew(T, n)        ((T *)xmalloc_((size_t)(n) * sizeof(T), __FILE__, __LINE__))
+#define xnew0(T, n)       ((T *)xcalloc_((size_t)(n) * sizeof(T), __FILE__, __LINE__))
+#define xgrow(T, p, n)    ((T *)xrealloc_((p), (size_t)(n) * sizeof(T), __FILE__, __LINE__))
+
+/* ---- sorting (sort.c) --------------------------------------------------- */
+/* Stable LSD radix sort of (key,val) pairs on the low `bits` bits of key.
+   tmpk/tmpv are scratch of n entries; result ends up back in key/val.      */
+void xsort_u64_u32(u64 *key, u32 *val, size_t n, unsigned bits,
+                   u64 *tmpk, u32 *tmpv);
+/* Stable sort of a permutation: perm is reordered so key[perm[.]] ascends.  */
+void xsort_perm_u32(u32 *perm, const u32 *key, size_t n, u32 maxkey);
+void xsort_perm_u64(u32 *perm, const u64 *key, size_t n, u64 maxkey);
+
+/* ---- local topology (topo.c) -------------------------------------------- */
+/* One row per nonzero local label, ordered by (primary, flag, index): the
+   order the reference establishes in nonzero_ids(), src/gs.upc:87-112.      */
+struct xg_topo {
+  size_t nnz;         /* rows */
+  u64   *id;          /* |label| of each group                [ngrp] */
+  u32   *idx;         /* local index i                        [nnz] */
+  unsigned char *flag;/* label was negative                   [nnz] */
+  size_t ngrp;        /* distinct labels on this rank (singletons included) */
+  u32   *gstart;      /* row offset of each label group       [ngrp+1] */
+};
+void xg_topo_build(struct xg_topo *t, const i64 *id, size_t n);
+void xg_topo_free(struct xg_topo *t);
+
+/* host CSR of gather/scatter groups (only groups with >= 2 members) plus the
+   list of flagged primaries; replaces the three sentinel streams built by
+   local_setup(), src/gs.upc:1210-1217.                                      */
+struct xg_hmap {
+  u32  ng, ni;
+  u32 *off;           /* [ng+1] */
+  u32 *idx;           /* [ni] members: primary first, unflagged before flagged */
+  u32 *nunf;          /* [ng] unflagged members per group (NULL: all unflagged) */
+};
+void xg_hmap_free(struct xg_hmap *m);
+void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m);
+u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *count);
+
+/* ---- world / communicator (comm.c) -------------------------------------- */
+struct xg_world;
+struct xg_world *xg_world_get(void);           /* creates on first use */
+int   xg_world_rank(const struct xg_world *w);
+int   xg_world_np(const struct xg_world *w);
+int   xg_world_has_cuda(const struct xg_world *w);
+void *xg_world_stream(struct xg_world *w, int which);   /* 0 main, 1 comm */
+void *xg_world_event(struct xg_world *w, int which);
+void *xg_world_nccl(struct xg_world *w);       /* ncclComm_t, created lazily */
+/* grow-only device scratch areas owned by the world (the analogue of the
+   reference's file-static buffer, src/gs.upc:35): 0 send, 1 recv, 2 stage   */
+void *xg_world_scratch(struct xg_world *w, int which, size_t bytes);
+
+/* host-side collectives over the rendezvous segment (np>1) */
+void  xg_host_barrier(struct xg_world *w);
+/* every rank contributes `bytes` bytes; out receives np*bytes, rank-major   */
+void  xg_host_allgather(struct xg_world *w, const void *in, size_t bytes, void *out);
+/* rows of `rowbytes` bytes, already grouped by destination: sendcnt[p] rows
+   go to rank p.  Returns a malloc'd array of received rows ordered by source
+   rank; *nrecv rows, recvcnt[p] (caller array of np) from each source.      */
+void *xg_host_alltoallv(struct xg_world *w, const void *rows, size_t rowbytes,
+                        const size_t *sendcnt, size_t *recvcnt, size_t *nrecv);
+
+/* ---- CUDA side (gs_cuda.cu), thin C ABI used by the host C code ---------- */
+int    xcu_device_count(void);
+int    xcu_set_device(int dev);
+void  *xcu_malloc(size_t bytes);
+void   xcu_free(void *p);
+void   xcu_h2d(void *dst, const void *src, size_t bytes, void *stream);
+void   xcu_d2h(void *dst, const void *src, size_t bytes, void *stream);
+void   xcu_d2d(void *dst, const void *src, size_t bytes, void *stream);
+void   xcu_memset(void *dst, int byte, size_t bytes, void *stream);
+int    xcu_is_device_ptr(const void *p);
+void  *xcu_stream_create(int high_priority);
+void   xcu_stream_destroy(void *s);
+void   xcu_stream_sync(void *s);
+void  *xcu_event_create(void);
+void   xcu_event_record(void *ev, void *stream);
+void   xcu_stream_wait_event(void *stream, void *ev);
+void   xcu_device_sync(void);
+void  *xcu_host_alloc(size_t bytes);
+void   xcu_host_free(void *p);
+unsigned long long xcu_launch_count(void);
+
+/* a field as the kernels see it */
+struct xcu_field {
+  void    *p[XG_MAXV];   /* plain/vec: p[0]; many: one pointer per component */
+  unsigned vn;           /* components handled by this launch               */
+  unsigned tuple;        /* vec: elements per tuple in memory (>= vn)       */
+  unsigned k0;           /* vec: first component handled by this launch     */
+};
+
+/* device CSR */
+struct xcu_csr {
+  u32 ng, ni;
+  const u32 *off, *idx, *nunf;   /* device pointers; nunf may be NULL */
+};
+
+/* boundary description on the device (np>1) */
+struct xcu_bnd {
+  u32 nb;                        /* boundary primaries */
+  const u32 *goff, *gidx, *nunf; /* members of each (>=1), unflagged count   */
+  const u32 *soff[2], *slot[2];  /* pairwise buffer slots per direction      */
+  const u32 *ord;                /* all-reduce slot per boundary primary     */
+  const unsigned char *pflag;    /* primary flagged?                          */
+};
+
+/* fused local gather(+init)+scatter over every group of m                  */
+void xcu_fused(void *stream, const struct xcu_csr *m, const struct xcu_field *f,
+               int mode, int xdom, int xop, int transpose);
+/* out[list[j]] = identity(op) for the flagged primaries that head no group */
+void xcu_init_list(void *stream, const u32 *list, u32 n, const struct xcu_field *f,
+                   int mode, int xdom, int xop);
+/* boundary: local gather (+init) -> u[primary] and -> sendbuf slots (dir) */
+void xcu_bnd_pack(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
+                  int mode, int xdom, int xop, int transpose, void *sendbuf,
+                  unsigned bufvn, int allreduce);
+/* boundary: fold recvbuf slots into u[primary], then scatter to members    */
+void xcu_bnd_unpack(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
+                    int mode, int xdom, int xop, int transpose, const void *recvbuf,
+                    unsigned bufvn, int allreduce);
+void xcu_fill_identity(void *stream, void *out, size_t n, int xdom, int xop);
+void xcu_array_op(void *stream, void *out, const void *in, size_t n, int xdom, int xop);
+/* generic CSR gather / scatter between two (possibly different) fields:
+   used by the public gs_local.h entry points.                              */
+void xcu_csr_gather(void *stream, const struct xcu_csr *m, const struct xcu_field *out,
+                    int omode, const struct xcu_field *in, int imode,
+                    int xdom, int xop);
+void xcu_csr_scatter(void *stream, const struct xcu_csr *m, const struct xcu_field *out,
+                     int omode, const struct xcu_field *in, int imode, int xdom);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

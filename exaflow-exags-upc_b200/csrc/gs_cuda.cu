@@ -1,0 +1,509 @@
+// gs_cuda.cu -- sm_100a kernels for the gs_op hot path and the thin C ABI the
+// host C code calls them through.
+//
+// What the kernels replace (reference paths relative to /root/reference):
+//   k_fused        gather_T_OP + init_T + scatter_T run back to back by
+//                  gs_aux (src/gs.upc:1181-1184, src/gs_local.c:60-97) --
+//                  one pass over a CSR map instead of two passes over a
+//                  sentinel stream, each group reduced left to right by one
+//                  thread so the association order is the reference's.
+//   k_bnd_pack     local gather of boundary groups + scatter_to_buf
+//                  (src/gs.upc:490, src/gs_local.c:76-87,308-318)
+//   k_bnd_unpack   gather_from_buf + local scatter (src/gs.upc:499,1184)
+//   k_fill/k_array gs_init_array / gs_gather_array (src/gs_local.c:187-201)
+//   k_csr_gather / k_csr_scatter   the public gs_local.h entry points
+//
+// The path is HBM-bound integer/floating "a OP= b" work on irregular index
+// sets: no tensor cores, no GEMM reshaping.  See DESIGN.md for the roofline.
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include "exags_internal.h"
+
+// ---------------------------------------------------------------------------
+// error funnel: every CUDA failure ends in the reference's fail() contract
+// ---------------------------------------------------------------------------
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      exags_fail(1, __FILE__, __LINE__, "CUDA error: %s (%s)",                \
+                 cudaGetErrorString(e_), #call);                              \
+  } while (0)
+
+static unsigned long long g_launches = 0;
+#define LAUNCHED() do { ++g_launches; CU(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------------------
+// monoid definitions (src/gs_defs.h:33-52)
+// ---------------------------------------------------------------------------
+template <typename T> struct Lim;
+template <> struct Lim<double>    { static __host__ __device__ double    hi() { return DBL_MAX; }  static __host__ __device__ double    lo() { return -DBL_MAX; } };
+template <> struct Lim<float>     { static __host__ __device__ float     hi() { return FLT_MAX; }  static __host__ __device__ float     lo() { return -FLT_MAX; } };
+template <> struct Lim<int>       { static __host__ __device__ int       hi() { return INT_MAX; }  static __host__ __device__ int       lo() { return INT_MIN; } };
+template <> struct Lim<long long> { static __host__ __device__ long long hi() { return LLONG_MAX; } static __host__ __device__ long long lo() { return LLONG_MIN; } };
+
+template <typename T, int OP>
+__host__ __device__ __forceinline__ T ident()
+{
+  if (OP == XO_MUL) return (T)1;
+  if (OP == XO_MIN) return Lim<T>::hi();
+  if (OP == XO_MAX) return Lim<T>::lo();
+  return (T)0;   // add, bpr
+}
+
+// a OP= b with the reference's exact comparison forms (not fmin/fmax)
+template <typename T, int OP>
+__device__ __forceinline__ T apply(T a, T b)
+{
+  if (OP == XO_ADD) return a + b;
+  if (OP == XO_MUL) return a * b;
+  if (OP == XO_MIN) return (b < a) ? b : a;
+  if (OP == XO_MAX) return (b > a) ? b : a;
+  // binary-prefix (src/gs_defs.h:37-42): longest common leading bit string
+  if (b != (T)0) {
+    unsigned a_ = (unsigned)a, b_ = (unsigned)b;
+    if (a_ == 0u) return (T)b_;
+    for (;;) { if (a_ < b_) b_ >>= 1; else if (b_ < a_) a_ >>= 1; else break; }
+    return (T)a_;
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------------------
+// field addressing: plain T[n], vec T[n][tuple], many T*[vn]
+// ---------------------------------------------------------------------------
+template <typename T, int MODE>
+struct Fld {
+  T *p[XG_MAXV];
+  unsigned vn, tuple, k0;
+  __device__ __forceinline__ T *at(u32 i, unsigned k) const
+  {
+    if (MODE == XM_PLAIN) return p[0] + i;
+    if (MODE == XM_VEC)   return p[0] + (size_t)i * tuple + k0 + k;
+    return p[k] + i;
+  }
+};
+
+template <typename T, int MODE>
+static Fld<T, MODE> make_fld(const xcu_field *f)
+{
+  Fld<T, MODE> r;
+  for (int k = 0; k < XG_MAXV; ++k) r.p[k] = (T *)f->p[k];
+  r.vn = f->vn; r.tuple = f->tuple; r.k0 = f->k0;
+  return r;
+}
+
+// runtime-mode variant for the non-hot public gs_local.h kernels
+template <typename T>
+struct FldR {
+  T *p[XG_MAXV];
+  unsigned vn, tuple, k0; int mode;
+  __device__ __forceinline__ T *at(u32 i, unsigned k) const
+  {
+    if (mode == XM_PLAIN) return p[0] + i;
+    if (mode == XM_VEC)   return p[0] + (size_t)i * tuple + k0 + k;
+    return p[k] + i;
+  }
+};
+template <typename T>
+static FldR<T> make_fldr(const xcu_field *f, int mode)
+{
+  FldR<T> r;
+  for (int k = 0; k < XG_MAXV; ++k) r.p[k] = (T *)f->p[k];
+  r.vn = f->vn; r.tuple = f->tuple; r.k0 = f->k0; r.mode = mode;
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// one group: reduce members [0,nred) left to right, write members [0,nwr)
+// ---------------------------------------------------------------------------
+#define GRP_REG 8   // members kept in registers; SEM hex meshes have 2/4/8
+
+template <typename T, int OP, int MODE>
+__device__ __forceinline__ void group_fused(const Fld<T, MODE> &f, const u32 *__restrict__ idx,
+                                            u32 nall, u32 nred, u32 nwr)
+{
+  if (nall <= GRP_REG) {
+    u32 id[GRP_REG];
+#pragma unroll
+    for (int j = 0; j < GRP_REG; ++j) id[j] = (j < (int)nall) ? __ldg(idx + j) : 0u;
+    for (unsigned k = 0; k < f.vn; ++k) {
+      T x[GRP_REG];
+#pragma unroll
+      for (int j = 0; j < GRP_REG; ++j) if (j < (int)nred) x[j] = *f.at(id[j], k);
+      T v = nred ? x[0] : ident<T, OP>();
+#pragma unroll
+      for (int j = 1; j < GRP_REG; ++j) if (j < (int)nred) v = apply<T, OP>(v, x[j]);
+#pragma unroll
+      for (int j = 0; j < GRP_REG; ++j) if (j < (int)nwr) *f.at(id[j], k) = v;
+    }
+  } else {
+    for (unsigned k = 0; k < f.vn; ++k) {
+      T v = nred ? *f.at(__ldg(idx), k) : ident<T, OP>();
+      for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, *f.at(__ldg(idx + j), k));
+      for (u32 j = 0; j < nwr; ++j) *f.at(__ldg(idx + j), k) = v;
+    }
+  }
+}
+
+// reference semantics of one gs() on a group with nall members of which the
+// first nunf are unflagged (src/gs.upc:1181-1184):
+//   transpose==0: reduce the unflagged members (identity if none: the primary
+//                 is a flagged primary and gs_init overwrites it), write all
+//   transpose==1: reduce all members, write the primary and the unflagged
+__device__ __forceinline__ void group_counts(u32 nall, u32 nunf, int transpose, u32 &nred, u32 &nwr)
+{
+  if (transpose) { nred = nall; nwr = nunf > 1u ? nunf : 1u; }
+  else           { nred = nunf; nwr = nall; }
+}
+
+template <typename T, int OP, int MODE>
+__global__ void __launch_bounds__(256)
+k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
+{
+  u32 g = blockIdx.x * 256u + threadIdx.x;
+  if (g >= m.ng) return;
+  u32 b = __ldg(m.off + g), e = __ldg(m.off + g + 1);
+  u32 nall = e - b, nunf = m.nunf ? __ldg(m.nunf + g) : nall, nred, nwr;
+  group_counts(nall, nunf, transpose, nred, nwr);
+  group_fused<T, OP, MODE>(f, m.idx + b, nall, nred, nwr);
+}
+
+template <typename T, int OP, int MODE>
+__global__ void __launch_bounds__(256)
+k_init_list(const u32 *__restrict__ list, u32 n, Fld<T, MODE> f)
+{
+  u32 j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= n) return;
+  u32 i = __ldg(list + j);
+  for (unsigned k = 0; k < f.vn; ++k) *f.at(i, k) = ident<T, OP>();
+}
+
+// boundary primaries: gather -> u[primary] and -> send slots
+template <typename T, int OP, int MODE>
+__global__ void __launch_bounds__(256)
+k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
+           unsigned bufvn, int allreduce)
+{
+  u32 b = blockIdx.x * 256u + threadIdx.x;
+  if (b >= bd.nb) return;
+  u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
+  u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
+  group_counts(nall, nunf, transpose, nred, nwr);
+  const u32 *idx = bd.gidx + gb;
+  u32 prim = __ldg(idx);
+  const int sd = 1 ^ transpose;                 // send map (src/gs.upc:479)
+  u32 sb = 0, se = 0, ord = 0; bool contributes = true;
+  if (allreduce) {
+    ord = __ldg(bd.ord + b);
+    // map_to_buf (src/gs.upc:1059,1063): flagged primaries stay out unless transposed
+    contributes = transpose || !bd.pflag[b];
+  } else {
+    sb = __ldg(bd.soff[sd] + b); se = __ldg(bd.soff[sd] + b + 1);
+  }
+  for (unsigned k = 0; k < f.vn; ++k) {
+    T v = nred ? *f.at(prim, k) : ident<T, OP>();
+    for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, *f.at(__ldg(idx + j), k));
+    *f.at(prim, k) = v;
+    if (allreduce) {
+      if (contributes) sendbuf[(size_t)ord * bufvn + f.k0 + k] = v;
+    } else {
+      for (u32 s = sb; s < se; ++s)
+        sendbuf[(size_t)__ldg(bd.slot[sd] + s) * bufvn + f.k0 + k] = v;
+    }
+  }
+}
+
+// boundary primaries: fold received slots in ascending remote rank, scatter
+template <typename T, int OP, int MODE>
+__global__ void __launch_bounds__(256)
+k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ recvbuf,
+             unsigned bufvn, int allreduce)
+{
+  u32 b = blockIdx.x * 256u + threadIdx.x;
+  if (b >= bd.nb) return;
+  u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
+  u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
+  group_counts(nall, nunf, transpose, nred, nwr);
+  const u32 *idx = bd.gidx + gb;
+  u32 prim = __ldg(idx);
+  const int rd = 0 ^ transpose;                 // recv map (src/gs.upc:479)
+  u32 rb = 0, re = 0, ord = 0; bool takes = true;
+  if (allreduce) {
+    ord = __ldg(bd.ord + b);
+    // map_from_buf (src/gs.upc:1060,1064)
+    takes = !transpose || !bd.pflag[b];
+  } else {
+    rb = __ldg(bd.soff[rd] + b); re = __ldg(bd.soff[rd] + b + 1);
+  }
+  for (unsigned k = 0; k < f.vn; ++k) {
+    T v = *f.at(prim, k);
+    if (allreduce) {
+      if (takes) v = recvbuf[(size_t)ord * bufvn + f.k0 + k];
+    } else {
+      for (u32 s = rb; s < re; ++s)
+        v = apply<T, OP>(v, recvbuf[(size_t)__ldg(bd.slot[rd] + s) * bufvn + f.k0 + k]);
+    }
+    for (u32 j = 0; j < nwr; ++j) *f.at(__ldg(idx + j), k) = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill(T *__restrict__ out, size_t n, T v)
+{
+  size_t i = (size_t)blockIdx.x * 256u + threadIdx.x;
+  size_t step = (size_t)gridDim.x * 256u;
+  for (; i < n; i += step) out[i] = v;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) k_array(T *__restrict__ out, const T *__restrict__ in, size_t n)
+{
+  size_t i = (size_t)blockIdx.x * 256u + threadIdx.x;
+  size_t step = (size_t)gridDim.x * 256u;
+  for (; i < n; i += step) out[i] = apply<T, OP>(out[i], in[i]);
+}
+
+// public gs_local.h kernels on a CSR built from a sentinel map:
+// member 0 of each group indexes `out`, the rest index `in`.
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+k_csr_gather(xcu_csr m, FldR<T> out, FldR<T> in)
+{
+  u32 g = blockIdx.x * 256u + threadIdx.x;
+  if (g >= m.ng) return;
+  u32 b = __ldg(m.off + g), e = __ldg(m.off + g + 1);
+  u32 dst = __ldg(m.idx + b);
+  for (unsigned k = 0; k < out.vn; ++k) {
+    T v = *out.at(dst, k);
+    for (u32 j = b + 1; j < e; ++j) v = apply<T, OP>(v, *in.at(__ldg(m.idx + j), k));
+    *out.at(dst, k) = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_csr_scatter(xcu_csr m, FldR<T> out, FldR<T> in)
+{
+  u32 g = blockIdx.x * 256u + threadIdx.x;
+  if (g >= m.ng) return;
+  u32 b = __ldg(m.off + g), e = __ldg(m.off + g + 1);
+  u32 src = __ldg(m.idx + b);
+  for (unsigned k = 0; k < out.vn; ++k) {
+    T v = *in.at(src, k);
+    for (u32 j = b + 1; j < e; ++j) *out.at(__ldg(m.idx + j), k) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dispatch helpers
+// ---------------------------------------------------------------------------
+static inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255u) / 256u); }
+
+#define FOR_OP(T, MODE, X)                                                    \
+  switch (xop) {                                                              \
+    case XO_ADD: X(T, XO_ADD, MODE); break;                                   \
+    case XO_MUL: X(T, XO_MUL, MODE); break;                                   \
+    case XO_MIN: X(T, XO_MIN, MODE); break;                                   \
+    case XO_MAX: X(T, XO_MAX, MODE); break;                                   \
+    case XO_BPR:                                                              \
+      if (xdom == XD_I32 || xdom == XD_I64) { X(T, XO_BPR, MODE); }           \
+      else exags_fail(1, __FILE__, __LINE__, "gs: gs_bpr is defined on integer domains only"); \
+      break;                                                                  \
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad op %d", xop);         \
+  }
+#define FOR_DOM(MODE, X)                                                      \
+  switch (xdom) {                                                             \
+    case XD_F64: FOR_OP(double, MODE, X); break;                              \
+    case XD_F32: FOR_OP(float, MODE, X); break;                               \
+    case XD_I32: FOR_OP(int, MODE, X); break;                                 \
+    case XD_I64: FOR_OP(long long, MODE, X); break;                           \
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad domain %d", xdom);    \
+  }
+#define FOR_ALL(X)                                                            \
+  switch (mode) {                                                             \
+    case XM_PLAIN: FOR_DOM(XM_PLAIN, X); break;                               \
+    case XM_VEC:   FOR_DOM(XM_VEC, X); break;                                 \
+    case XM_MANY:  FOR_DOM(XM_MANY, X); break;                                \
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad mode %d", mode);      \
+  }
+
+extern "C" {
+
+unsigned long long xcu_launch_count(void) { return g_launches; }
+
+void xcu_fused(void *stream, const xcu_csr *m, const xcu_field *f, int mode, int xdom, int xop,
+               int transpose)
+{
+  if (!m->ng) return;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(T, OP, MODE)                                                        \
+  k_fused<T, OP, MODE><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fld<T, MODE>(f), transpose)
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_init_list(void *stream, const u32 *list, u32 n, const xcu_field *f, int mode, int xdom,
+                   int xop)
+{
+  if (!n) return;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(T, OP, MODE)                                                        \
+  k_init_list<T, OP, MODE><<<blocks_for(n), 256, 0, st>>>(list, n, make_fld<T, MODE>(f))
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_bnd_pack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, int xdom, int xop,
+                  int transpose, void *sendbuf, unsigned bufvn, int allreduce)
+{
+  if (!b->nb) return;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(T, OP, MODE)                                                        \
+  k_bnd_pack<T, OP, MODE><<<blocks_for(b->nb), 256, 0, st>>>(                 \
+      *b, make_fld<T, MODE>(f), transpose, (T *)sendbuf, bufvn, allreduce)
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, int xdom,
+                    int xop, int transpose, const void *recvbuf, unsigned bufvn, int allreduce)
+{
+  if (!b->nb) return;
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(T, OP, MODE)                                                        \
+  k_bnd_unpack<T, OP, MODE><<<blocks_for(b->nb), 256, 0, st>>>(               \
+      *b, make_fld<T, MODE>(f), transpose, (const T *)recvbuf, bufvn, allreduce)
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_fill_identity(void *stream, void *out, size_t n, int xdom, int xop)
+{
+  if (!n) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned nb = blocks_for(n); if (nb > 148u * 8u) nb = 148u * 8u;
+  const int mode = XM_PLAIN;
+#define X(T, OP, MODE) k_fill<T><<<nb, 256, 0, st>>>((T *)out, n, ident<T, OP>())
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_array_op(void *stream, void *out, const void *in, size_t n, int xdom, int xop)
+{
+  if (!n) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned nb = blocks_for(n); if (nb > 148u * 8u) nb = 148u * 8u;
+  const int mode = XM_PLAIN;
+#define X(T, OP, MODE) k_array<T, OP><<<nb, 256, 0, st>>>((T *)out, (const T *)in, n)
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_csr_gather(void *stream, const xcu_csr *m, const xcu_field *out, int omode,
+                    const xcu_field *in, int imode, int xdom, int xop)
+{
+  if (!m->ng) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = XM_PLAIN;
+#define X(T, OP, MODE)                                                        \
+  k_csr_gather<T, OP><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fldr<T>(out, omode), make_fldr<T>(in, imode))
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_csr_scatter(void *stream, const xcu_csr *m, const xcu_field *out, int omode,
+                     const xcu_field *in, int imode, int xdom)
+{
+  if (!m->ng) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (xdom) {
+    case XD_F64: case XD_I64:
+      k_csr_scatter<long long><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fldr<long long>(out, omode), make_fldr<long long>(in, imode));
+      break;
+    case XD_F32: case XD_I32:
+      k_csr_scatter<int><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fldr<int>(out, omode), make_fldr<int>(in, imode));
+      break;
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad domain %d", xdom);
+  }
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------
+// runtime plumbing
+// ---------------------------------------------------------------------------
+int xcu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int xcu_set_device(int dev)
+{
+  CU(cudaSetDevice(dev));
+  CU(cudaFree(0));
+  return 0;
+}
+
+void *xcu_malloc(size_t bytes)
+{
+  void *p = 0;
+  CU(cudaMalloc(&p, bytes ? bytes : 1));
+  return p;
+}
+void xcu_free(void *p) { if (p) CU(cudaFree(p)); }
+void xcu_h2d(void *d, const void *s, size_t n, void *st)
+{ if (n) CU(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); }
+void xcu_d2h(void *d, const void *s, size_t n, void *st)
+{ if (n) CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); }
+void xcu_d2d(void *d, const void *s, size_t n, void *st)
+{ if (n) CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, (cudaStream_t)st)); }
+void xcu_memset(void *d, int byte, size_t n, void *st)
+{ if (n) CU(cudaMemsetAsync(d, byte, n, (cudaStream_t)st)); }
+
+int xcu_is_device_ptr(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+void *xcu_stream_create(int high_priority)
+{
+  cudaStream_t s;
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+  return (void *)s;
+}
+void xcu_stream_destroy(void *s) { if (s) CU(cudaStreamDestroy((cudaStream_t)s)); }
+void xcu_stream_sync(void *s) { CU(cudaStreamSynchronize((cudaStream_t)s)); }
+void *xcu_event_create(void)
+{
+  cudaEvent_t e;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return (void *)e;
+}
+void xcu_event_record(void *ev, void *st) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
+void xcu_stream_wait_event(void *st, void *ev) { CU(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0)); }
+void xcu_device_sync(void) { CU(cudaDeviceSynchronize()); }
+void *xcu_host_alloc(size_t bytes)
+{
+  void *p = 0;
+  CU(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return p;
+}
+void xcu_host_free(void *p) { if (p) CU(cudaFreeHost(p)); }
+
+} // extern "C"

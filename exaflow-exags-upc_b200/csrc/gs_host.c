@@ -1,0 +1,673 @@
+/* gs_host.c -- gs_setup / gs / gs_vec / gs_many / gs_free / gs_unique, the
+ * Fortran bindings and the public gs_local.h entry points.
+ *
+ * Host driver of the hot path.  The reference's gs_aux (src/gs.upc:1169-1185)
+ * runs four serial passes per call: local gather, init, remote exec, local
+ * scatter.  Here one call is
+ *
+ *   np == 1:  one fused kernel over the CSR map in HBM (+ a tiny init kernel
+ *             when flagged singletons exist);
+ *   np  > 1:  groups are split at setup into interior (no remote sharer) and
+ *             boundary.  Boundary work -- gather+pack, NCCL grouped
+ *             send/recv over NVLink, unpack+scatter -- runs on a
+ *             high-priority stream while the fused interior kernel runs on
+ *             the caller's stream; an event joins the two.
+ *
+ * There is no CPU execution path: without a CUDA device gs() fails loudly.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "exags_internal.h"
+#include "gs_plan.h"
+
+struct dev_csr { struct xcu_csr c; u32 *off, *idx, *nunf; };
+
+struct gs_data {
+  comm_ptr comm;
+  struct xg_world *w;
+  u32 n;
+  int method;                 /* method in use (never gs_auto) */
+  int on_device;
+  /* host copies, kept for exags_gs_dump_map / exags_gs_info */
+  struct xg_hmap hall;        /* every group with >= 2 members */
+  u32 *hfp; u32 nfp;          /* all flagged primaries (src/gs.upc:359-370) */
+  struct xg_plan plan;        /* np > 1 */
+  u64 sectors_f64;            /* distinct 32-byte sectors of a double field touched */
+  /* device */
+  struct dev_csr d_int;       /* interior groups (all groups when np == 1) */
+  u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
+  struct xcu_bnd d_bnd;       /* boundary primaries */
+  void *d_bnd_mem[10];
+  size_t handle_bytes;
+};
+
+/* ------------------------------------------------------------------ */
+static void *upload(const void *src, size_t bytes)
+{
+  void *d = xcu_malloc(bytes);
+  xcu_h2d(d, src, bytes, 0);
+  return d;
+}
+
+static void upload_csr(struct dev_csr *d, const struct xg_hmap *m)
+{
+  memset(d, 0, sizeof *d);
+  d->c.ng = m->ng; d->c.ni = m->ni;
+  if (!m->ng) return;
+  d->off = (u32 *)upload(m->off, ((size_t)m->ng + 1) * sizeof(u32));
+  d->idx = (u32 *)upload(m->idx, (size_t)m->ni * sizeof(u32));
+  if (m->nunf) d->nunf = (u32 *)upload(m->nunf, (size_t)m->ng * sizeof(u32));
+  d->c.off = d->off; d->c.idx = d->idx; d->c.nunf = d->nunf;
+}
+
+static u64 count_sectors(const struct xg_hmap *m, unsigned elem_bytes)
+{
+  /* distinct 32-byte sectors of a T[n] field holding a participating DOF;
+     members of different groups are distinct indices, so mark and count */
+  u64 cnt = 0;
+  if (!m->ni) return 0;
+  u32 maxi = 0;
+  for (u32 k = 0; k < m->ni; ++k) if (m->idx[k] > maxi) maxi = m->idx[k];
+  size_t nsec = ((size_t)maxi * elem_bytes) / 32 + 1;
+  unsigned char *mark = xnew0(unsigned char, nsec);
+  for (u32 k = 0; k < m->ni; ++k) mark[((size_t)m->idx[k] * elem_bytes) / 32] = 1;
+  for (size_t s = 0; s < nsec; ++s) cnt += mark[s];
+  free(mark);
+  return cnt;
+}
+
+/* ------------------------------------------------------------------ */
+/*  exchange (np > 1)                                                  */
+/* ------------------------------------------------------------------ */
+static void exchange_pairwise(struct gs_data *g, unsigned vn, int xd, int transpose,
+                              void *sendbuf, void *recvbuf, void *stream)
+{
+  const struct xg_plan *pl = &g->plan;
+  const int sd = 1 ^ transpose, rd = 0 ^ transpose;   /* src/gs.upc:479 */
+  const size_t unit = (size_t)vn * xg_dom_bytes(xd);
+  if (!pl->nnb[sd] && !pl->nnb[rd]) return;
+  xg_nccl_group_start(g->w);
+  for (u32 k = 0; k < pl->nnb[rd]; ++k)
+    xg_nccl_recv(g->w, (char *)recvbuf + (size_t)pl->nb_start[rd][k] * unit,
+                 (size_t)pl->nb_size[rd][k] * vn, xd, (int)pl->nb_rank[rd][k], stream);
+  for (u32 k = 0; k < pl->nnb[sd]; ++k)
+    xg_nccl_send(g->w, (char *)sendbuf + (size_t)pl->nb_start[sd][k] * unit,
+                 (size_t)pl->nb_size[sd][k] * vn, xd, (int)pl->nb_rank[sd][k], stream);
+  xg_nccl_group_end(g->w);
+}
+
+/* ------------------------------------------------------------------ */
+/*  the operator                                                       */
+/* ------------------------------------------------------------------ */
+static void check_dom_op(int dom, int op, int *xd, const char *who)
+{
+  *xd = xg_dom_of(dom);
+  if (*xd < 0) xfail("%s: datatype %d not in valid range", who, dom);
+  if (op < 0 || op >= XO_N) xfail("%s: op %d not in valid range", who, op);
+}
+
+/* Enqueue one gs on device-resident data.  ptrs: vn device pointers for
+   mode many, else ptrs[0].  Work is ordered on `stream`.                   */
+static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
+                       int xd, int xop, int transpose, void *stream)
+{
+  struct xg_world *w = g->w;
+  const int multi = xg_world_np(w) > 1 && (g->plan.nb > 0 || g->method == gs_all_reduce);
+  const int allred = g->method == gs_all_reduce;
+  const unsigned esz = xg_dom_bytes(xd);
+  void *scomm = 0, *sendbuf = 0, *recvbuf = 0;
+
+  if (multi) {
+    const struct xg_plan *pl = &g->plan;
+    scomm = xg_world_stream(w, 1);
+    if (allred) {
+      sendbuf = xg_world_scratch(w, 0, (size_t)pl->total_shared * vn * esz);
+      recvbuf = sendbuf;
+    } else {
+      sendbuf = xg_world_scratch(w, 0, (size_t)pl->total[1 ^ transpose] * vn * esz);
+      recvbuf = xg_world_scratch(w, 1, (size_t)pl->total[0 ^ transpose] * vn * esz);
+    }
+    /* fork: boundary stream starts after whatever precedes us on `stream` */
+    xcu_event_record(xg_world_event(w, 0), stream);
+    xcu_stream_wait_event(scomm, xg_world_event(w, 0));
+    if (allred) xcu_fill_identity(scomm, sendbuf, (size_t)pl->total_shared * vn, xd, xop);
+  }
+
+  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
+  /* boundary: gather + pack */
+  if (multi)
+    for (unsigned k0 = 0; k0 < vn; k0 += step) {
+      struct xcu_field f; memset(&f, 0, sizeof f);
+      f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = (mode == XM_MANY) ? k0 : 0;
+      if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
+      else f.p[0] = ptrs[0];
+      xcu_bnd_pack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, sendbuf, vn, allred);
+    }
+  /* interior: fused gather-scatter on the caller's stream */
+  for (unsigned k0 = 0; k0 < vn; k0 += step) {
+    struct xcu_field f; memset(&f, 0, sizeof f);
+    f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = 0;
+    if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
+    else f.p[0] = ptrs[0];
+    xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
+    if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
+  }
+  if (multi) {
+    if (allred) xg_nccl_allreduce(w, sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
+    else exchange_pairwise(g, vn, xd, transpose, sendbuf, recvbuf, scomm);
+    for (unsigned k0 = 0; k0 < vn; k0 += step) {
+      struct xcu_field f; memset(&f, 0, sizeof f);
+      f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = (mode == XM_MANY) ? k0 : 0;
+      if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
+      else f.p[0] = ptrs[0];
+      xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, recvbuf, vn, allred);
+    }
+    /* join */
+    xcu_event_record(xg_world_event(w, 1), scomm);
+    xcu_stream_wait_event(stream, xg_world_event(w, 1));
+  }
+}
+
+static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned transpose,
+                   struct gs_data *g, void *stream, int blocking, const char *who)
+{
+  int xd;
+  if (!g) xfail("%s: null handle", who);
+  check_dom_op(dom, op, &xd, who);
+  if (!g->on_device)
+    xfail("%s: no CUDA device -- this library has no CPU execution path", who);
+  if (vn == 0) return;
+  transpose = transpose != 0;
+  struct xg_world *w = g->w;
+  if (!stream) stream = xg_world_stream(w, 0);
+  const size_t esz = xg_dom_bytes(xd), n = g->n;
+
+  void **ptrs = xnew(void *, vn);
+  int host = 0;
+  if (mode == XM_MANY) {
+    void *const *tab = (void *const *)u;
+    for (unsigned k = 0; k < vn; ++k) ptrs[k] = tab[k];
+    host = !xcu_is_device_ptr(ptrs[0]);
+    for (unsigned k = 1; k < vn; ++k)
+      if ((!xcu_is_device_ptr(ptrs[k])) != host)
+        xfail("%s: gs_many arrays must be all host or all device", who);
+  } else {
+    ptrs[0] = u;
+    host = !xcu_is_device_ptr(u);
+  }
+
+  if (!host) {
+    gs_enqueue(g, ptrs, mode, vn, xd, op, (int)transpose, stream);
+    if (blocking) xcu_stream_sync(stream);
+    free(ptrs);
+    return;
+  }
+  /* host data: stage through HBM (still GPU compute) */
+  size_t each = n * esz, total = each * vn;
+  char *stage = (char *)xg_world_scratch(w, 2, total);
+  void **dptr = xnew(void *, vn);
+  if (mode == XM_MANY) {
+    for (unsigned k = 0; k < vn; ++k) { dptr[k] = stage + each * k; xcu_h2d(dptr[k], ptrs[k], each, stream); }
+  } else {
+    dptr[0] = stage; xcu_h2d(stage, u, total, stream);
+  }
+  gs_enqueue(g, dptr, mode, vn, xd, op, (int)transpose, stream);
+  if (mode == XM_MANY) for (unsigned k = 0; k < vn; ++k) xcu_d2h(ptrs[k], dptr[k], each, stream);
+  else xcu_d2h(u, stage, total, stream);
+  xcu_stream_sync(stream);
+  free(dptr); free(ptrs);
+}
+
+void exags_gs(void *u, gs_dom dom, gs_op_t op, unsigned transpose, struct gs_data *gsh, buffer *buf)
+{ (void)buf; gs_run(u, XM_PLAIN, 1, (int)dom, (int)op, transpose, gsh, 0, 1, "gs"); }
+
+void exags_gs_vec(void *u, unsigned vn, gs_dom dom, gs_op_t op, unsigned transpose,
+                  struct gs_data *gsh, buffer *buf)
+{ (void)buf; gs_run(u, XM_VEC, vn, (int)dom, (int)op, transpose, gsh, 0, 1, "gs_vec"); }
+
+void exags_gs_many(void *const *u, unsigned vn, gs_dom dom, gs_op_t op, unsigned transpose,
+                   struct gs_data *gsh, buffer *buf)
+{ (void)buf; gs_run((void *)u, XM_MANY, vn, (int)dom, (int)op, transpose, gsh, 0, 1, "gs_many"); }
+
+void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op, unsigned transpose,
+                    struct gs_data *gsh, void *stream)
+{
+  if (mode < XM_PLAIN || mode > XM_MANY) xfail("gs_async: bad mode %d", mode);
+  if (mode == XM_PLAIN) vn = 1;
+  gs_run(u, mode, vn, dom, op, transpose, gsh, stream, 0, "gs_async");
+}
+
+/* the Nek flavour shares the operator; only the id width differs */
+void gslib_gs(void *u, int dom, int op, unsigned t, struct gs_data *g, buffer *b)
+{ (void)b; gs_run(u, XM_PLAIN, 1, dom, op, t, g, 0, 1, "gs"); }
+void gslib_gs_vec(void *u, unsigned vn, int dom, int op, unsigned t, struct gs_data *g, buffer *b)
+{ (void)b; gs_run(u, XM_VEC, vn, dom, op, t, g, 0, 1, "gs_vec"); }
+void gslib_gs_many(void *const *u, unsigned vn, int dom, int op, unsigned t, struct gs_data *g, buffer *b)
+{ (void)b; gs_run((void *)u, XM_MANY, vn, dom, op, t, g, 0, 1, "gs_many"); }
+
+/* ------------------------------------------------------------------ */
+/*  setup                                                              */
+/* ------------------------------------------------------------------ */
+static void split_groups(struct gs_data *g, const struct xg_topo *t)
+{
+  /* interior CSR = groups (>= 2 members) whose primary is not a boundary
+     primary; boundary CSR = all members of each boundary primary's group */
+  const struct xg_plan *pl = &g->plan;
+  const u32 nb = pl->nb;
+  int any_flag = g->hall.nunf != 0;
+  struct xg_hmap in; memset(&in, 0, sizeof in);
+  size_t ng = 0, ni = 0, nfs = 0, bni = 0;
+  {
+    u32 b = 0;
+    for (size_t gi = 0; gi < t->ngrp; ++gi) {
+      u32 a = t->gstart[gi], e = t->gstart[gi + 1];
+      if (b < nb && pl->bgrp[b] == gi) { ++b; bni += e - a; continue; }
+      if (e - a >= 2) { ++ng; ni += e - a; }
+      else if (t->flag[a]) ++nfs;
+    }
+  }
+  in.ng = (u32)ng; in.ni = (u32)ni;
+  in.off = xnew(u32, ng + 1);
+  in.idx = xnew(u32, ni ? ni : 1);
+  if (any_flag) in.nunf = xnew(u32, ng ? ng : 1);
+  u32 *fs = xnew(u32, nfs ? nfs : 1);
+  u32 *bgoff = xnew(u32, (size_t)nb + 1), *bgidx = xnew(u32, bni ? bni : 1), *bnunf = xnew(u32, nb ? nb : 1);
+  {
+    u32 b = 0; size_t og = 0, oi = 0, of = 0, ob = 0;
+    for (size_t gi = 0; gi < t->ngrp; ++gi) {
+      u32 a = t->gstart[gi], e = t->gstart[gi + 1], unf = 0;
+      for (u32 j = a; j < e && !t->flag[j]; ++j) ++unf;
+      if (b < nb && pl->bgrp[b] == gi) {
+        bgoff[b] = (u32)ob; bnunf[b] = unf;
+        memcpy(bgidx + ob, t->idx + a, (size_t)(e - a) * sizeof(u32));
+        ob += e - a; ++b;
+        continue;
+      }
+      if (e - a >= 2) {
+        in.off[og] = (u32)oi;
+        if (in.nunf) in.nunf[og] = unf;
+        memcpy(in.idx + oi, t->idx + a, (size_t)(e - a) * sizeof(u32));
+        oi += e - a; ++og;
+      } else if (t->flag[a]) fs[of++] = t->idx[a];
+    }
+    in.off[ng] = (u32)oi;
+    bgoff[nb] = (u32)ob;
+  }
+  g->nfs = (u32)nfs;
+  if (g->on_device) {
+    upload_csr(&g->d_int, &in);
+    if (nfs) g->d_fs = (u32 *)upload(fs, nfs * sizeof(u32));
+    if (nb) {
+      int m = 0;
+      struct xcu_bnd *d = &g->d_bnd;
+      d->nb = nb;
+#define UP(dst, src, cnt) do { g->d_bnd_mem[m] = upload((src), (size_t)(cnt) * sizeof(*(src))); (dst) = g->d_bnd_mem[m]; ++m; } while (0)
+      UP(d->goff, bgoff, nb + 1);
+      UP(d->gidx, bgidx, bni ? bni : 1);
+      UP(d->nunf, bnunf, nb);
+      for (int dd = 0; dd < 2; ++dd) {
+        UP(d->soff[dd], pl->soff[dd], nb + 1);
+        UP(d->slot[dd], pl->slot[dd], pl->total[dd] ? pl->total[dd] : 1);
+      }
+      UP(d->ord, pl->ord, nb);
+      UP(d->pflag, pl->pflag, nb);
+#undef UP
+    }
+    xcu_device_sync();
+  } else {
+    g->d_int.c.ng = in.ng; g->d_int.c.ni = in.ni;
+  }
+  g->handle_bytes += ((size_t)ng + 1 + ni + nfs + nb + 1 + bni + nb) * sizeof(u32);
+  xg_hmap_free(&in); free(fs); free(bgoff); free(bgidx); free(bnunf);
+}
+
+/* time the exchange step alone, the way dry_run_time does
+   (src/gs.upc:1094-1111): 2 warm-ups, 10 timed, mean; max over ranks */
+static double time_exchange(struct gs_data *g, int method)
+{
+  struct xg_world *w = g->w;
+  int save = g->method;
+  g->method = method;
+  const struct xg_plan *pl = &g->plan;
+  void *s = xg_world_stream(w, 1);
+  size_t nsend = method == gs_all_reduce ? (size_t)pl->total_shared : pl->total[1];
+  size_t nrecv = method == gs_all_reduce ? 0 : pl->total[0];
+  void *sb = xg_world_scratch(w, 0, nsend * 8), *rb = xg_world_scratch(w, 1, nrecv * 8);
+  xcu_memset(sb, 0, nsend * 8, s);
+  double t0 = 0, t1 = 0;
+  for (int it = 0; it < 12; ++it) {
+    if (it == 2) { xcu_stream_sync(s); xg_host_barrier(w); exags_comm_time(&t0); }
+    if (method == gs_all_reduce) xg_nccl_allreduce(w, sb, nsend, XD_F64, XO_ADD, s);
+    else exchange_pairwise(g, 1, XD_F64, 0, sb, rb, s);
+  }
+  xcu_stream_sync(s);
+  exags_comm_time(&t1);
+  double t = (t1 - t0) / 10, buf;
+  exags_comm_allreduce(g->comm, gs_double, gs_max, &t, 1, &buf);
+  g->method = save;
+  return t;
+}
+
+static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, int unique,
+                                  int method, int verbose)
+{
+  if (!comm) xfail("gs_setup: null communicator");
+  if (method < gs_auto || method > gs_all_reduce) xfail("gs_setup: bad method %d", method);
+  struct gs_data *g = xnew0(struct gs_data, 1);
+  exags_comm_dup(&g->comm, comm);
+  struct xg_world *w = (struct xg_world *)comm->priv;
+  g->w = w; g->n = n;
+  g->on_device = xg_world_has_cuda(w);
+  if (!g->on_device) {
+    const char *ho = getenv("EXAGS_HOST_SETUP_ONLY");
+    if (!(ho && atoi(ho)))
+      xfail("gs_setup: no CUDA device available; this library has no CPU path "
+            "(set EXAGS_HOST_SETUP_ONLY=1 only to inspect the host-side maps)");
+  }
+  const int np = comm->np;
+  const i64 *id = id_in;
+  i64 *id_own = 0;
+  struct xg_topo topo;
+  struct xg_shared sh;
+  xg_topo_build(&topo, id, n);
+  xg_shared_discover(&sh, &topo, w);
+  if (unique) {
+    /* same outcome as gs_unique followed by a plain setup (src/gs.h) */
+    unsigned char *nf = xnew(unsigned char, n ? n : 1);
+    xg_unique_flags(nf, n, &topo, &sh, comm->id);
+    id_own = xnew(i64, n ? n : 1);
+    for (u32 i = 0; i < n; ++i) {
+      i64 a = id_in[i] < 0 ? -id_in[i] : id_in[i];
+      id_own[i] = nf[i] ? -a : a;
+    }
+    free(nf);
+    xg_topo_free(&topo); xg_shared_free(&sh);
+    id = id_own;
+    xg_topo_build(&topo, id, n);
+    xg_shared_discover(&sh, &topo, w);
+  }
+
+  xg_topo_local_map(&topo, 1, &g->hall);
+  g->hfp = xg_topo_flagged_primaries(&topo, 0, &g->nfp);
+  g->sectors_f64 = count_sectors(&g->hall, 8);
+  g->handle_bytes = sizeof *g;
+
+  xg_plan_build(&g->plan, &sh, &topo);
+  split_groups(g, &topo);
+  xg_shared_free(&sh);
+  xg_topo_free(&topo);
+  free(id_own);
+
+  if (verbose && comm->id == 0)
+    printf("gs_setup: %ld unique labels shared\n", (long)g->plan.total_shared);
+
+  /* method: crystal-router requests run the direct pairwise exchange -- on
+     one NVSwitch domain every peer is one hop away, so log-P routing has
+     nothing to save */
+  g->method = method == gs_all_reduce ? gs_all_reduce : gs_pairwise;
+  if (method == gs_auto && np > 1 && g->on_device) {
+    double tp = time_exchange(g, gs_pairwise);
+    const char *name = "pairwise";
+    if (comm->id == 0) printf("   pairwise times (avg, min, max): %g %g %g\n", tp, tp, tp);
+    if (g->plan.total_shared < 100000) {    /* src/gs.upc:1146 */
+      double ta = time_exchange(g, gs_all_reduce);
+      if (comm->id == 0) printf("   all reduce                    : %g %g %g\n", ta, ta, ta);
+      if (ta < tp) { g->method = gs_all_reduce; name = "allreduce"; }
+    }
+    if (comm->id == 0) printf("   used all_to_all method: %s\n", name);
+  }
+  if (g->method == gs_all_reduce && np > 1 && g->plan.total_shared > 0xFFFFFFFFull)
+    xfail("gs_setup: too many shared labels for the all-reduce method");
+
+  if (verbose) {
+    double avg[2], tmp[2];
+    int mn[2], mx[2], ti[2];
+    size_t bufvals = g->method == gs_all_reduce ? 2 * (size_t)g->plan.total_shared
+                                                : (size_t)g->plan.total[0] + g->plan.total[1];
+    avg[0] = (double)g->handle_bytes / np; avg[1] = 8.0 * (double)bufvals / np;
+    mn[0] = mx[0] = (int)g->handle_bytes; mn[1] = mx[1] = (int)(8 * bufvals);
+    exags_comm_allreduce(g->comm, gs_double, gs_add, avg, 2, tmp);
+    exags_comm_allreduce(g->comm, gs_int, gs_min, mn, 2, ti);
+    exags_comm_allreduce(g->comm, gs_int, gs_max, mx, 2, ti);
+    if (comm->id == 0) {
+      printf("   handle bytes (avg, min, max): %g %u %u\n", avg[0], (unsigned)mn[0], (unsigned)mx[0]);
+      printf("   buffer bytes (avg, min, max): %g %u %u\n", avg[1], (unsigned)mn[1], (unsigned)mx[1]);
+    }
+  }
+  fflush(stdout);
+  return g;
+}
+
+struct gs_data *gslib_gs_setup(const long long *id, exags_uint n, const comm_ptr comm,
+                               int unique, int method, int verbose)
+{
+  return setup_core((const i64 *)id, n, comm, unique, method, verbose);
+}
+
+struct gs_data *exags_gs_setup(const int *id, exags_uint n, const comm_ptr comm, int unique,
+                               gs_method method, int verbose)
+{
+  i64 *wide = xnew(i64, n ? n : 1);
+  for (exags_uint i = 0; i < n; ++i) wide[i] = id[i];
+  struct gs_data *g = setup_core(wide, n, comm, unique, (int)method, verbose);
+  free(wide);
+  return g;
+}
+
+void exags_gs_free(struct gs_data *g)
+{
+  if (!g) return;
+  if (g->on_device) {
+    xcu_device_sync();
+    xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
+    xcu_free(g->d_fs);
+    for (int m = 0; m < 10; ++m) xcu_free(g->d_bnd_mem[m]);
+  }
+  xg_hmap_free(&g->hall);
+  free(g->hfp);
+  xg_plan_free(&g->plan);
+  exags_comm_free(&g->comm);
+  free(g);
+}
+void gslib_gs_free(struct gs_data *g) { exags_gs_free(g); }
+
+static void unique_core(i64 *id, u32 n, const comm_ptr comm)
+{
+  if (!comm) xfail("gs_unique: null communicator");
+  struct xg_world *w = (struct xg_world *)comm->priv;
+  struct xg_topo topo; struct xg_shared sh;
+  xg_topo_build(&topo, id, n);
+  xg_shared_discover(&sh, &topo, w);
+  unsigned char *nf = xnew(unsigned char, n ? n : 1);
+  xg_unique_flags(nf, n, &topo, &sh, comm->id);
+  for (u32 i = 0; i < n; ++i)
+    if (nf[i] && id[i] > 0) id[i] = -id[i];
+  free(nf);
+  xg_shared_free(&sh); xg_topo_free(&topo);
+}
+
+void gslib_gs_unique(long long *id, exags_uint n, const comm_ptr comm) { unique_core((i64 *)id, n, comm); }
+
+void exags_gs_unique(int *id, exags_uint n, const comm_ptr comm)
+{
+  i64 *wide = xnew(i64, n ? n : 1);
+  for (exags_uint i = 0; i < n; ++i) wide[i] = id[i];
+  unique_core(wide, n, comm);
+  for (exags_uint i = 0; i < n; ++i) id[i] = (int)wide[i];
+  free(wide);
+}
+
+/* ------------------------------------------------------------------ */
+/*  introspection                                                      */
+/* ------------------------------------------------------------------ */
+void exags_gs_info(const struct gs_data *g, unsigned long long what[16])
+{
+  memset(what, 0, 16 * sizeof what[0]);
+  what[0] = g->n; what[1] = g->hall.ng; what[2] = g->hall.ni; what[3] = g->nfp;
+  what[4] = g->plan.nnb[0] > g->plan.nnb[1] ? g->plan.nnb[0] : g->plan.nnb[1];
+  what[5] = g->plan.total[1]; what[6] = g->plan.total[0];
+  what[7] = g->plan.total_shared; what[8] = (unsigned long long)g->method;
+  what[9] = g->sectors_f64; what[10] = g->plan.nb; what[11] = g->d_int.c.ng;
+  what[12] = g->d_int.c.ni; what[13] = g->nfs; what[14] = g->handle_bytes;
+}
+
+size_t exags_gs_dump_map(const struct gs_data *g, int which, exags_uint *out, size_t cap)
+{
+  size_t o = 0;
+#define PUT(v) do { if (o < cap) out[o] = (v); ++o; } while (0)
+  if (which == 0 || which == 1) {
+    const struct xg_hmap *m = &g->hall;
+    for (u32 gi = 0; gi < m->ng; ++gi) {
+      u32 a = m->off[gi], e = m->off[gi + 1];
+      u32 cnt = e - a;
+      if (which == 0 && m->nunf) {
+        /* unflagged members only; the head is the primary even when flagged,
+           but then nothing follows and the group is dropped */
+        u32 unf = m->nunf[gi];
+        cnt = unf >= 1 ? unf : 1;
+      }
+      if (cnt < 2) continue;
+      for (u32 j = 0; j < cnt; ++j) PUT(m->idx[a + j]);
+      PUT(XG_NONE);
+    }
+    PUT(XG_NONE);
+  } else if (which == 2) {
+    for (u32 k = 0; k < g->nfp; ++k) PUT(g->hfp[k]);
+    PUT(XG_NONE);
+  } else if (which == 3 || which == 4) {
+    const struct xg_plan *pl = &g->plan;
+    int d = which - 3;
+    for (u32 b = 0; b < pl->nb; ++b) {
+      u32 a = pl->soff[d] ? pl->soff[d][b] : 0, e = pl->soff[d] ? pl->soff[d][b + 1] : 0;
+      if (a == e) continue;
+      PUT(pl->bprim[b]);
+      for (u32 s = a; s < e; ++s) PUT(pl->slot[d][s]);
+      PUT(XG_NONE);
+    }
+    PUT(XG_NONE);
+  }
+#undef PUT
+  return o;
+}
+
+unsigned long long exags_kernel_launches(void) { return xcu_launch_count(); }
+
+void *exags_device_malloc(size_t bytes) { xg_world_get(); return xcu_malloc(bytes); }
+void exags_device_free(void *p) { xcu_free(p); }
+void exags_memcpy_h2d(void *d, const void *s, size_t n) { xcu_h2d(d, s, n, 0); xcu_device_sync(); }
+void exags_memcpy_d2h(void *d, const void *s, size_t n) { xcu_d2h(d, s, n, 0); xcu_device_sync(); }
+void exags_device_sync(void) { xcu_device_sync(); }
+void *exags_host_malloc_pinned(size_t bytes) { xg_world_get(); return xcu_host_alloc(bytes); }
+void exags_host_free_pinned(void *p) { xcu_host_free(p); }
+
+/* ------------------------------------------------------------------ */
+/*  Fortran bindings (src/gs.upc:1309-1418)                            */
+/* ------------------------------------------------------------------ */
+static struct gs_data **fgs_info = 0;
+static int fgs_max = 0, fgs_n = 0;
+
+static int fgs_new(struct gs_data *g)
+{
+  if (fgs_n == fgs_max) {
+    fgs_max += fgs_max / 2 + 1;
+    fgs_info = xgrow(struct gs_data *, fgs_info, fgs_max);
+  }
+  fgs_info[fgs_n] = g;
+  return fgs_n++;
+}
+
+static void fgs_check(int handle, int dom, int op, int with_parms, const char *func, unsigned line)
+{
+  if (with_parms) {
+    if (dom < 1 || dom > 3) exags_fail(1, __FILE__, line, "%s: datatype %d not in valid range 1-3", func, dom);
+    if (op < 1 || op > 4) exags_fail(1, __FILE__, line, "%s: op %d not in valid range 1-4", func, op);
+  }
+  if (handle < 0 || handle >= fgs_n || !fgs_info[handle])
+    exags_fail(1, __FILE__, line, "%s: invalid handle", func);
+}
+
+/* Fortran dom 1..3 = {double, sint, slong}; slong is 32-bit in the default
+   flavour and 64-bit in the Nek flavour (src/gs.upc:1352, src/types.h:60-76) */
+static int fdom(int dom, int wide) { return dom == 1 ? gs_double : dom == 2 ? gs_int : (wide ? 4 : gs_int); }
+static size_t fdom_bytes(int dom, int wide) { return dom == 1 ? 8 : dom == 2 ? 4 : (wide ? 8 : 4); }
+
+#define FGS_BODY_SETUP(IDT, SETUP, METHOD)                                    \
+  exags_comm_init();                                                          \
+  *handle = fgs_new(SETUP((const IDT *)id, (exags_uint)*n, exags_glb_comm, 0, METHOD, 1))
+
+void exags_fgs_setup(int *handle, const int id[], const int *n, const int *comm, const int *np)
+{ (void)comm; (void)np; FGS_BODY_SETUP(int, exags_gs_setup, gs_auto); }
+void exags_fgs_setup_pick(int *handle, const int id[], const int *n, const int *comm, const int *np, const int *method)
+{ (void)comm; (void)np; FGS_BODY_SETUP(int, exags_gs_setup, (gs_method)*method); }
+void fgslib_gs_setup_(int *handle, const long long id[], const int *n, const int *comm, const int *np)
+{ (void)comm; (void)np; FGS_BODY_SETUP(long long, gslib_gs_setup, gs_auto); }
+void fgslib_gs_setup_pick_(int *handle, const long long id[], const int *n, const int *comm, const int *np, const int *method)
+{ (void)comm; (void)np; FGS_BODY_SETUP(long long, gslib_gs_setup, *method); }
+
+static void fgs_op(int wide, const int *handle, void *u, const int *dom, const int *op, const int *transpose)
+{
+  fgs_check(*handle, *dom, *op, 1, "gs_op", __LINE__);
+  gs_run(u, XM_PLAIN, 1, fdom(*dom, wide), *op - 1, *transpose != 0, fgs_info[*handle], 0, 1, "gs_op");
+}
+static void fgs_op_vec(int wide, const int *handle, void *u, const int *n, const int *dom, const int *op, const int *transpose)
+{
+  fgs_check(*handle, *dom, *op, 1, "gs_op_vec", __LINE__);
+  gs_run(u, XM_VEC, (unsigned)*n, fdom(*dom, wide), *op - 1, *transpose != 0, fgs_info[*handle], 0, 1, "gs_op_vec");
+}
+static void fgs_op_many(int wide, const int *handle, void *u1, void *u2, void *u3, void *u4, void *u5, void *u6,
+                        const int *n, const int *dom, const int *op, const int *transpose)
+{
+  void *uu[6] = { u1, u2, u3, u4, u5, u6 };
+  fgs_check(*handle, *dom, *op, 1, "gs_op_many", __LINE__);
+  if (*n < 0 || *n > 6) xfail("gs_op_many: %d arrays, at most 6", *n);
+  gs_run((void *)uu, XM_MANY, (unsigned)*n, fdom(*dom, wide), *op - 1, *transpose != 0, fgs_info[*handle], 0, 1, "gs_op_many");
+}
+static void fgs_op_fields(int wide, const int *handle, void *u, const int *stride, const int *n,
+                          const int *dom, const int *op, const int *transpose)
+{
+  fgs_check(*handle, *dom, *op, 1, "gs_op_fields", __LINE__);
+  if (*n <= 0) return;
+  void **p = xnew(void *, *n);
+  size_t offset = (size_t)*stride * fdom_bytes(*dom, wide);
+  for (int k = 0; k < *n; ++k) p[k] = (char *)u + offset * (size_t)k;
+  gs_run((void *)p, XM_MANY, (unsigned)*n, fdom(*dom, wide), *op - 1, *transpose != 0, fgs_info[*handle], 0, 1, "gs_op_fields");
+  free(p);
+}
+static void fgs_release(const int *handle)
+{
+  fgs_check(*handle, 0, 0, 0, "gs_free", __LINE__);
+  exags_gs_free(fgs_info[*handle]);
+  fgs_info[*handle] = 0;
+}
+
+void exags_fgs(const int *h, void *u, const int *d, const int *o, const int *t) { fgs_op(0, h, u, d, o, t); }
+void exags_fgs_vec(const int *h, void *u, const int *n, const int *d, const int *o, const int *t) { fgs_op_vec(0, h, u, n, d, o, t); }
+void exags_fgs_many(const int *h, void *u1, void *u2, void *u3, void *u4, void *u5, void *u6, const int *n, const int *d, const int *o, const int *t)
+{ fgs_op_many(0, h, u1, u2, u3, u4, u5, u6, n, d, o, t); }
+void exags_fgs_fields(const int *h, void *u, const int *s, const int *n, const int *d, const int *o, const int *t) { fgs_op_fields(0, h, u, s, n, d, o, t); }
+void exags_fgs_free(const int *h) { fgs_release(h); }
+
+void fgslib_gs_op_(const int *h, void *u, const int *d, const int *o, const int *t) { fgs_op(1, h, u, d, o, t); }
+void fgslib_gs_op_vec_(const int *h, void *u, const int *n, const int *d, const int *o, const int *t) { fgs_op_vec(1, h, u, n, d, o, t); }
+void fgslib_gs_op_many_(const int *h, void *u1, void *u2, void *u3, void *u4, void *u5, void *u6, const int *n, const int *d, const int *o, const int *t)
+{ fgs_op_many(1, h, u1, u2, u3, u4, u5, u6, n, d, o, t); }
+void fgslib_gs_op_fields_(const int *h, void *u, const int *s, const int *n, const int *d, const int *o, const int *t) { fgs_op_fields(1, h, u, s, n, d, o, t); }
+void fgslib_gs_free_(const int *h) { fgs_release(h); }
+
+/* default-flavour Fortran spellings: bare and with trailing underscore
+   (FORTRAN_NAME, src/name.h:32-41) */
+#define FALIAS(name, target) \
+  extern __typeof__(target) name __attribute__((alias(#target)))
+FALIAS(gs_setup_, exags_fgs_setup);
+FALIAS(gs_setup_pick_, exags_fgs_setup_pick);
+FALIAS(gs_op_, exags_fgs);
+FALIAS(gs_op_vec_, exags_fgs_vec);
+FALIAS(gs_op_many_, exags_fgs_many);
+FALIAS(gs_op_fields_, exags_fgs_fields);
+FALIAS(gs_free_, exags_fgs_free);
+FALIAS(gs_setup_pick, exags_fgs_setup_pick);
+FALIAS(gs_op, exags_fgs);
+FALIAS(gs_op_vec, exags_fgs_vec);
+FALIAS(gs_op_many, exags_fgs_many);
+FALIAS(gs_op_fields, exags_fgs_fields);

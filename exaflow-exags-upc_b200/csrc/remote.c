@@ -1,0 +1,299 @@
+/* remote.c -- discovery of labels shared between ranks and the pairwise /
+ * all-reduce exchange plans.
+ *
+ * Restates, on the host in C as the north star prescribes:
+ *   unique_ids + shared_ids + shared_ids_aux   src/gs.upc:117-244
+ *   make_topology_unique (owner choice)         src/gs.upc:253-322
+ *   pw_comm_setup + pw_map_setup                src/gs.upc:505-570
+ *   allreduce_map_setup                         src/gs.upc:1031-1050
+ *
+ * The reference routes rows with a log-P crystal router over UPC puts
+ * (src/sarray_transfer.upc:137-180); on one node every rank reaches every
+ * other directly, so the same rendezvous ("work rank" = id mod np) is done
+ * with one all-to-all over the host shared-memory segment each way.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "exags_internal.h"
+#include "gs_plan.h"
+
+struct uq_row { u64 id; u32 src_if; u32 pad; };                 /* to work rank   */
+struct wk_row { u64 id, ord; u32 p2, i1f, i2f, pad; };          /* back to source */
+
+static inline u32 unflag(u32 v) { return (~v < v) ? ~v : v; }   /* src/gs.upc:176 */
+static inline int is_flagged(u32 v) { return ~v < v; }
+
+static unsigned nbits64(u64 v) { unsigned b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
+
+/* ------------------------------------------------------------------ */
+void xg_shared_free(struct xg_shared *s)
+{
+  free(s->row);
+  memset(s, 0, sizeof *s);
+}
+
+void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w)
+{
+  const int np = xg_world_np(w), me = xg_world_rank(w);
+  memset(out, 0, sizeof *out);
+  if (np == 1) return;
+
+  /* one row per local label, grouped by work rank id % np (src/gs.upc:118-131) */
+  size_t *cnt = xnew0(size_t, np), *pos = xnew(size_t, np);
+  for (size_t g = 0; g < t->ngrp; ++g) ++cnt[t->id[g] % (u64)np];
+  { size_t run = 0; for (int p = 0; p < np; ++p) { pos[p] = run; run += cnt[p]; } }
+  struct uq_row *send = xnew(struct uq_row, t->ngrp ? t->ngrp : 1);
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g];
+    struct uq_row *r = send + pos[t->id[g] % (u64)np]++;
+    r->id = t->id[g];
+    r->src_if = t->flag[a] ? ~t->idx[a] : t->idx[a];
+    r->pad = 0;
+  }
+  size_t *rcnt = xnew(size_t, np), nrecv = 0;
+  struct uq_row *un = (struct uq_row *)xg_host_alltoallv(w, send, sizeof *send, cnt, rcnt, &nrecv);
+  free(send);
+
+  /* work rank: group by id with unflagged rows ahead of flagged ones
+     (src/gs.upc:204).  Rows arrive ordered by source rank. */
+  u32 *src = xnew(u32, nrecv ? nrecv : 1);
+  { size_t o = 0; for (int p = 0; p < np; ++p) for (size_t k = 0; k < rcnt[p]; ++k) src[o++] = (u32)p; }
+  u32 *perm = xnew(u32, nrecv ? nrecv : 1);
+  {
+    size_t o = 0;
+    for (size_t k = 0; k < nrecv; ++k) if (!is_flagged(un[k].src_if)) perm[o++] = (u32)k;
+    for (size_t k = 0; k < nrecv; ++k) if (is_flagged(un[k].src_if)) perm[o++] = (u32)k;
+  }
+  u64 *ids = xnew(u64, nrecv ? nrecv : 1), maxid = 0;
+  for (size_t k = 0; k < nrecv; ++k) { ids[k] = un[k].id; if (ids[k] > maxid) maxid = ids[k]; }
+  xsort_perm_u64(perm, ids, nrecv, maxid);
+  free(ids);
+
+  /* count shared labels (src/gs.upc:206-212): an unflagged first row with at
+     least one more row behind it */
+  u64 n_shared = 0;
+  size_t nwork = 0;
+  for (size_t a = 0; a < nrecv;) {
+    size_t b = a + 1;
+    while (b < nrecv && un[perm[b]].id == un[perm[a]].id) ++b;
+    if (b - a >= 2 && !is_flagged(un[perm[a]].src_if)) {
+      ++n_shared;
+      size_t nu = 0;
+      for (size_t k = a; k < b; ++k) nu += !is_flagged(un[perm[k]].src_if);
+      /* pairs with at least one unflagged side, both directions */
+      size_t L = b - a;
+      nwork += 2 * (nu * (nu - 1) / 2 + nu * (L - nu));
+    }
+    a = b;
+  }
+  /* global ordinal of each shared label (comm_scan, src/gs.upc:213) */
+  u64 *all_ns = xnew(u64, np);
+  xg_host_allgather(w, &n_shared, sizeof n_shared, all_ns);
+  u64 ord0 = 0, total = 0;
+  for (int p = 0; p < np; ++p) { if (p < me) ord0 += all_ns[p]; total += all_ns[p]; }
+  free(all_ns);
+
+  /* emit the pair rows (src/gs.upc:218-236), then group them by destination */
+  struct wk_row *wk = xnew(struct wk_row, nwork ? nwork : 1);
+  u32 *dst = xnew(u32, nwork ? nwork : 1);
+  size_t nw = 0;
+  u64 ord = ord0;
+  for (size_t a = 0; a < nrecv;) {
+    size_t b = a + 1;
+    while (b < nrecv && un[perm[b]].id == un[perm[a]].id) ++b;
+    if (b - a >= 2 && !is_flagged(un[perm[a]].src_if)) {
+      for (size_t x = a; x < b; ++x) {
+        const struct uq_row *rx = un + perm[x];
+        if (is_flagged(rx->src_if)) break;
+        for (size_t y = x + 1; y < b; ++y) {
+          const struct uq_row *ry = un + perm[y];
+          u32 p1 = src[perm[x]], p2 = src[perm[y]];
+          wk[nw].id = rx->id; wk[nw].ord = ord; wk[nw].p2 = p2; wk[nw].i1f = rx->src_if; wk[nw].i2f = ry->src_if; wk[nw].pad = 0; dst[nw] = p1; ++nw;
+          wk[nw].id = rx->id; wk[nw].ord = ord; wk[nw].p2 = p1; wk[nw].i1f = ry->src_if; wk[nw].i2f = rx->src_if; wk[nw].pad = 0; dst[nw] = p2; ++nw;
+        }
+      }
+      ++ord;
+    }
+    a = b;
+  }
+  free(perm); free(src); free(un);
+
+  memset(cnt, 0, (size_t)np * sizeof *cnt);
+  for (size_t k = 0; k < nw; ++k) ++cnt[dst[k]];
+  { size_t run = 0; for (int p = 0; p < np; ++p) { pos[p] = run; run += cnt[p]; } }
+  struct wk_row *wsend = xnew(struct wk_row, nw ? nw : 1);
+  for (size_t k = 0; k < nw; ++k) wsend[pos[dst[k]]++] = wk[k];
+  free(wk); free(dst);
+  size_t nback = 0;
+  struct wk_row *back = (struct wk_row *)xg_host_alltoallv(w, wsend, sizeof *wsend, cnt, rcnt, &nback);
+  free(wsend); free(cnt); free(pos); free(rcnt);
+
+  /* translate to shared rows (src/gs.upc:163-188) */
+  out->n = nback;
+  out->total_shared = total;
+  out->row = xnew(struct xg_shared_row, nback ? nback : 1);
+  for (size_t k = 0; k < nback; ++k) {
+    struct xg_shared_row *s = out->row + k;
+    s->id = back[k].id; s->ord = back[k].ord;
+    s->i = unflag(back[k].i1f); s->p = back[k].p2; s->ri = unflag(back[k].i2f);
+    s->flags = (is_flagged(back[k].i1f) ? XG_FLAGS_LOCAL : 0u) | (is_flagged(back[k].i2f) ? XG_FLAGS_REMOTE : 0u);
+  }
+  free(back);
+}
+
+/* sort shared rows by (p, id): the globally consistent message order
+   (src/gs.upc:510-511) */
+static void sort_rows_p_id(struct xg_shared *s)
+{
+  size_t n = s->n;
+  if (n < 2) return;
+  u32 *perm = xnew(u32, n);
+  u64 *key = xnew(u64, n), maxk = 0;
+  for (size_t k = 0; k < n; ++k) { perm[k] = (u32)k; key[k] = s->row[k].id; if (key[k] > maxk) maxk = key[k]; }
+  xsort_perm_u64(perm, key, n, maxk);
+  maxk = 0;
+  for (size_t k = 0; k < n; ++k) { key[k] = s->row[k].p; if (key[k] > maxk) maxk = key[k]; }
+  xsort_perm_u64(perm, key, n, maxk);
+  struct xg_shared_row *r2 = xnew(struct xg_shared_row, n);
+  for (size_t k = 0; k < n; ++k) r2[k] = s->row[perm[k]];
+  free(s->row); s->row = r2;
+  free(perm); free(key);
+}
+
+/* ------------------------------------------------------------------ */
+/* gs_unique: which local labels end up flagged (src/gs.upc:253-322).
+   newflag[i] = 1 marks local index i as flagged afterwards.             */
+void xg_unique_flags(unsigned char *newflag, size_t n, const struct xg_topo *t,
+                     struct xg_shared *sh, int me)
+{
+  memset(newflag, 0, n);
+  /* keep existing flags; flag every local non-primary (src/gs.upc:262-271) */
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g], b = t->gstart[g + 1];
+    newflag[t->idx[a]] = t->flag[a];
+    for (u32 j = a + 1; j < b; ++j) newflag[t->idx[j]] = 1;
+  }
+  /* owner among the ranks sharing a label: the (id mod count)-th unflagged
+     sharer in rank order (src/gs.upc:279-302) */
+  sort_rows_p_id(sh);               /* by p, then group by i below */
+  size_t ns = sh->n;
+  if (!ns) return;
+  u32 *perm = xnew(u32, ns), *key = xnew(u32, ns), maxi = 0;
+  for (size_t k = 0; k < ns; ++k) { perm[k] = (u32)k; key[k] = sh->row[k].i; if (key[k] > maxi) maxi = key[k]; }
+  xsort_perm_u32(perm, key, ns, maxi);   /* stable: same i stays ordered by p */
+  free(key);
+  for (size_t a = 0; a < ns;) {
+    size_t b = a;
+    const struct xg_shared_row *first = sh->row + perm[a];
+    u32 lt = 0, gt = 0;
+    while (b < ns && sh->row[perm[b]].i == first->i) {
+      const struct xg_shared_row *r = sh->row + perm[b];
+      if (!(r->flags & XG_FLAGS_REMOTE)) { if (r->p < (u32)me) ++lt; else ++gt; }
+      ++b;
+    }
+    int mine = 0;
+    if (!(first->flags & XG_FLAGS_LOCAL)) mine = (first->id % (u64)(lt + gt + 1)) == lt;
+    if (!mine) newflag[first->i] = 1;
+    a = b;
+  }
+  free(perm);
+}
+
+/* ------------------------------------------------------------------ */
+void xg_plan_free(struct xg_plan *pl)
+{
+  free(pl->bprim); free(pl->bgrp);
+  for (int d = 0; d < 2; ++d) {
+    free(pl->soff[d]); free(pl->slot[d]);
+    free(pl->nb_rank[d]); free(pl->nb_start[d]); free(pl->nb_size[d]);
+  }
+  free(pl->ord); free(pl->pflag);
+  memset(pl, 0, sizeof *pl);
+}
+
+/* Exchange plan for this rank.  Boundary primaries are the distinct local
+   indices that appear in a shared row.  For each direction d the slots are
+   numbered over the rows sorted by (p,id) that pass the mask
+   (d==0: remote unflagged, d==1: local unflagged), src/gs.upc:505-535.     */
+void xg_plan_build(struct xg_plan *pl, struct xg_shared *sh, const struct xg_topo *t)
+{
+  memset(pl, 0, sizeof *pl);
+  pl->total_shared = sh->total_shared;
+  size_t ns = sh->n;
+  sort_rows_p_id(sh);
+
+  /* boundary primaries, ascending */
+  u32 *perm = xnew(u32, ns ? ns : 1), *key = xnew(u32, ns ? ns : 1), maxi = 0;
+  for (size_t k = 0; k < ns; ++k) { perm[k] = (u32)k; key[k] = sh->row[k].i; if (key[k] > maxi) maxi = key[k]; }
+  xsort_perm_u32(perm, key, ns, maxi);           /* by i, ties keep (p,id) order */
+  free(key);
+  u32 nb = 0;
+  for (size_t k = 0; k < ns; ++k) nb += (k == 0 || sh->row[perm[k]].i != sh->row[perm[k - 1]].i);
+  pl->nb = nb;
+  pl->bprim = xnew(u32, nb ? nb : 1);
+  pl->bgrp = xnew(u32, nb ? nb : 1);
+  pl->ord = xnew(u32, nb ? nb : 1);
+  pl->pflag = xnew(unsigned char, nb ? nb : 1);
+  u32 *bof = xnew(u32, ns ? ns : 1);             /* boundary number of each row */
+  {
+    u32 b = 0;
+    for (size_t k = 0; k < ns; ++k) {
+      const struct xg_shared_row *r = sh->row + perm[k];
+      if (k && r->i != sh->row[perm[k - 1]].i) ++b;
+      if (k == 0 || r->i != sh->row[perm[k - 1]].i) {
+        pl->bprim[b] = r->i;
+        if (r->ord >> 32) xfail("gs_setup: more than 2^32 shared labels");
+        pl->ord[b] = (u32)r->ord;
+        pl->pflag[b] = (r->flags & XG_FLAGS_LOCAL) ? 1 : 0;
+      }
+      bof[perm[k]] = b;
+    }
+  }
+  /* topology group of each boundary primary (both lists ascend by primary) */
+  {
+    size_t g = 0;
+    for (u32 b = 0; b < nb; ++b) {
+      while (g < t->ngrp && t->idx[t->gstart[g]] < pl->bprim[b]) ++g;
+      if (g >= t->ngrp || t->idx[t->gstart[g]] != pl->bprim[b])
+        xfail("gs_setup: shared label's primary index %u is not a local primary", pl->bprim[b]);
+      pl->bgrp[b] = (u32)g;
+    }
+  }
+
+  for (int d = 0; d < 2; ++d) {
+    const unsigned mask = d == 0 ? XG_FLAGS_REMOTE : XG_FLAGS_LOCAL;
+    /* slot numbers in (p,id) order; neighbour table */
+    u32 *bi = xnew(u32, ns ? ns : 1);
+    u32 count = 0, nn = 0, lastp = XG_NONE;
+    for (size_t k = 0; k < ns; ++k) {
+      const struct xg_shared_row *r = sh->row + k;
+      if (r->flags & mask) { bi[k] = XG_NONE; continue; }
+      bi[k] = count++;
+      if (r->p != lastp) { lastp = r->p; ++nn; }
+    }
+    pl->total[d] = count;
+    pl->nnb[d] = nn;
+    pl->nb_rank[d] = xnew(u32, nn ? nn : 1);
+    pl->nb_start[d] = xnew(u32, nn ? nn : 1);
+    pl->nb_size[d] = xnew0(u32, nn ? nn : 1);
+    nn = 0; lastp = XG_NONE;
+    for (size_t k = 0; k < ns; ++k) {
+      const struct xg_shared_row *r = sh->row + k;
+      if (bi[k] == XG_NONE) continue;
+      if (r->p != lastp) { lastp = r->p; pl->nb_rank[d][nn] = r->p; pl->nb_start[d][nn] = bi[k]; ++nn; }
+      ++pl->nb_size[d][nn - 1];
+    }
+    /* per boundary primary: its slots, ascending remote rank (src/gs.upc:546-570) */
+    pl->soff[d] = xnew0(u32, (size_t)nb + 1);
+    pl->slot[d] = xnew(u32, count ? count : 1);
+    for (size_t k = 0; k < ns; ++k) if (bi[k] != XG_NONE) ++pl->soff[d][bof[k] + 1];
+    for (u32 b = 0; b < nb; ++b) pl->soff[d][b + 1] += pl->soff[d][b];
+    u32 *fill = xnew(u32, nb ? nb : 1);
+    memcpy(fill, pl->soff[d], (size_t)nb * sizeof(u32));
+    for (size_t k = 0; k < ns; ++k)         /* rows are in (p,id) order */
+      if (bi[k] != XG_NONE) pl->slot[d][fill[bof[k]]++] = bi[k];
+    free(fill); free(bi);
+  }
+  free(bof); free(perm);
+  (void)nbits64;
+}

@@ -1,0 +1,172 @@
+/* topo.c -- local label topology and the local group maps.
+ *
+ * Restates what nonzero_ids() (src/gs.upc:87-112), local_map()
+ * (src/gs.upc:329-357) and flagged_primaries_map() (src/gs.upc:359-370)
+ * establish, with a different data layout:
+ *
+ *   reference: one 24-byte {id,i,flag,primary} row per nonzero label, two
+ *              stable struct sorts, then three sentinel-terminated uint
+ *              streams walked serially by the kernels;
+ *   here:      split key/payload arrays, one radix sort on (|id|,flag) and a
+ *              group-level sort on the primary index, then CSR arrays
+ *              (offsets + members) that go to HBM as they are.
+ *
+ * Ordering contract kept bit-for-bit, because it fixes the floating-point
+ * summation order: groups ascend by primary index; inside a group unflagged
+ * members come first, each class by ascending local index; the primary is the
+ * first member.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "exags_internal.h"
+
+void xg_topo_free(struct xg_topo *t)
+{
+  free(t->id); free(t->idx); free(t->flag); free(t->gstart);
+  memset(t, 0, sizeof *t);
+}
+
+void xg_hmap_free(struct xg_hmap *m)
+{
+  free(m->off); free(m->idx); free(m->nunf);
+  memset(m, 0, sizeof *m);
+}
+
+static unsigned nbits64(u64 v)
+{
+  unsigned b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b ? b : 1;
+}
+
+void xg_topo_build(struct xg_topo *t, const i64 *id, size_t n)
+{
+  memset(t, 0, sizeof *t);
+  if (n >= (size_t)XG_NONE)
+    xfail("gs_setup: local size %lu does not fit the 32-bit index type", (unsigned long)n);
+
+  /* rows for nonzero labels: key = |id|*2 + flagged, payload = index */
+  size_t nnz = 0;
+  for (size_t i = 0; i < n; ++i) nnz += (id[i] != 0);
+  u64 *key = xnew(u64, nnz), *tk = xnew(u64, nnz);
+  u32 *val = xnew(u32, nnz), *tv = xnew(u32, nnz);
+  u64 maxkey = 0;
+  size_t r = 0;
+  for (size_t i = 0; i < n; ++i) {
+    i64 v = id[i];
+    if (v == 0) continue;
+    u64 a = v < 0 ? (u64)(-(v + 1)) + 1u : (u64)v;
+    if (a >> 62) xfail("gs_setup: |id| = %llu is too large", (unsigned long long)a);
+    u64 k = (a << 1) | (u64)(v < 0);
+    key[r] = k; val[r] = (u32)i; ++r;
+    if (k > maxkey) maxkey = k;
+  }
+  /* (|id|, flag) ascending; stable => ascending index inside each class */
+  xsort_u64_u32(key, val, nnz, nbits64(maxkey), tk, tv);
+  free(tk); free(tv);
+
+  /* label groups in label order */
+  size_t ngrp = 0;
+  for (size_t j = 0; j < nnz; ++j)
+    ngrp += (j == 0 || (key[j] >> 1) != (key[j - 1] >> 1));
+  u32 *gs0 = xnew(u32, ngrp + 1);
+  u32 *prim = xnew(u32, ngrp ? ngrp : 1);
+  u32 maxprim = 0;
+  {
+    size_t g = 0;
+    for (size_t j = 0; j < nnz; ++j)
+      if (j == 0 || (key[j] >> 1) != (key[j - 1] >> 1)) {
+        gs0[g] = (u32)j; prim[g] = val[j];
+        if (val[j] > maxprim) maxprim = val[j];
+        ++g;
+      }
+    gs0[ngrp] = (u32)nnz;
+  }
+  /* order the groups by primary index (primaries are distinct) */
+  u32 *order = xnew(u32, ngrp ? ngrp : 1);
+  for (size_t g = 0; g < ngrp; ++g) order[g] = (u32)g;
+  xsort_perm_u32(order, prim, ngrp, maxprim);
+  free(prim);
+
+  t->nnz = nnz; t->ngrp = ngrp;
+  t->id = xnew(u64, ngrp ? ngrp : 1);
+  t->idx = xnew(u32, nnz ? nnz : 1);
+  t->flag = xnew(unsigned char, nnz ? nnz : 1);
+  t->gstart = xnew(u32, ngrp + 1);
+  {
+    u32 run = 0;
+    for (size_t g = 0; g < ngrp; ++g) {
+      u32 s = order[g];
+      t->gstart[g] = run;
+      run += gs0[s + 1] - gs0[s];
+    }
+    t->gstart[ngrp] = run;
+  }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (size_t g = 0; g < ngrp; ++g) {
+    u32 s = order[g], a = gs0[s], b = gs0[s + 1], o = t->gstart[g];
+    t->id[g] = key[a] >> 1;
+    for (u32 j = a; j < b; ++j, ++o) {
+      t->idx[o] = val[j];
+      t->flag[o] = (unsigned char)(key[j] & 1u);
+    }
+  }
+  free(order); free(gs0); free(key); free(val);
+}
+
+/* CSR of the groups with at least two members (src/gs.upc:329-357 emits a
+   group only when it has a second participant).  all != 0: every member
+   (map_local[1]); all == 0: unflagged members only (map_local[0]).
+   nunf is filled only for the `all` map and only if some label is flagged. */
+void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m)
+{
+  memset(m, 0, sizeof *m);
+  int any_flag = 0;
+  for (size_t j = 0; j < t->nnz && !any_flag; ++j) any_flag = t->flag[j];
+  size_t ng = 0, ni = 0;
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g], b = t->gstart[g + 1], cnt = 1;
+    if (all) cnt = b - a;
+    else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++cnt;
+    if (cnt >= 2) { ++ng; ni += cnt; }
+  }
+  if (ni >= (size_t)XG_NONE) xfail("gs_setup: local map too large");
+  m->ng = (u32)ng; m->ni = (u32)ni;
+  m->off = xnew(u32, ng + 1);
+  m->idx = xnew(u32, ni ? ni : 1);
+  if (all && any_flag) m->nunf = xnew(u32, ng ? ng : 1);
+  size_t og = 0, oi = 0;
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g], b = t->gstart[g + 1], cnt = 1, unf = 0;
+    for (u32 j = a; j < b && !t->flag[j]; ++j) ++unf;
+    if (all) cnt = b - a;
+    else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++cnt;
+    if (cnt < 2) continue;
+    m->off[og] = (u32)oi;
+    if (m->nunf) m->nunf[og] = unf;
+    memcpy(m->idx + oi, t->idx + a, (size_t)cnt * sizeof(u32));
+    oi += cnt; ++og;
+  }
+  m->off[ng] = (u32)oi;
+}
+
+/* indices of primaries whose label is flagged (src/gs.upc:359-370); when
+   singles_only != 0 keep only those that head no multi-member group.       */
+u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *count)
+{
+  size_t c = 0;
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g], b = t->gstart[g + 1];
+    if (t->flag[a] && (!singles_only || b - a == 1)) ++c;
+  }
+  u32 *out = xnew(u32, c ? c : 1);
+  size_t o = 0;
+  for (size_t g = 0; g < t->ngrp; ++g) {
+    u32 a = t->gstart[g], b = t->gstart[g + 1];
+    if (t->flag[a] && (!singles_only || b - a == 1)) out[o++] = t->idx[a];
+  }
+  *count = (u32)c;
+  return out;
+}

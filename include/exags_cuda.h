@@ -1,0 +1,57 @@
+/*
+ * exags_cuda.h -- B200 extensions to the reference API (SURVEY.md 8b
+ * "New-build addenda").  Nothing here exists in the reference; the blocking
+ * calls in exags.h are the drop-in surface.  Still a plain C ABI: a CUDA
+ * stream is passed as an opaque void* (a cudaStream_t).
+ */
+#ifndef EXAGS_CUDA_H
+#define EXAGS_CUDA_H
+
+#include "exags.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Stream-ordered gs on device-resident u: enqueues the kernels (and, for
+   np>1, the halo exchange) and returns without synchronising the host.
+   `stream` is a cudaStream_t; the work is ordered after what is already in
+   that stream and later work in that stream is ordered after it.
+   mode: 0 plain (u = T*), 1 vec (u = T[n][vn]), 2 many (u = host table of vn
+   device pointers).                                                        */
+void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op,
+                    unsigned transpose, struct gs_data *gsh, void *stream);
+
+/* Device selection (default: LOCAL_RANK mod device count, chosen in
+   comm_world).  Must be called before the first comm_world/comm_init.      */
+void exags_set_device(int device);
+int  exags_get_device(void);
+
+/* Introspection used by the parity tests and the bench.                    */
+/* Number of library kernels launched since process start.                  */
+unsigned long long exags_kernel_launches(void);
+/* Handle geometry: what[0]=n, [1]=groups G, [2]=member indices S,
+   [3]=flagged primaries, [4]=neighbour ranks, [5]=send slots, [6]=recv slots,
+   [7]=total_shared (low 32 bits), [8]=method in use, [9]=touched 32B sectors
+   of a double field (low 32 bits), [10]=boundary groups, [11]=interior groups */
+void exags_gs_info(const struct gs_data *gsh, unsigned long long what[16]);
+/* Write local map `which` (0 = unflagged members only, 1 = all members,
+   2 = flagged primaries, 3 = pairwise recv map, 4 = pairwise send map) in the
+   reference's sentinel format into out (capacity cap uints); returns the
+   length needed.  Lets tests compare setup against src/gs.upc:329-370,546-570. */
+size_t exags_gs_dump_map(const struct gs_data *gsh, int which,
+                         exags_uint *out, size_t cap);
+
+/* Device memory helpers so a C or Fortran caller needs no CUDA headers.    */
+void *exags_device_malloc(size_t bytes);
+void  exags_device_free(void *p);
+void  exags_memcpy_h2d(void *dst, const void *src, size_t bytes);
+void  exags_memcpy_d2h(void *dst, const void *src, size_t bytes);
+void  exags_device_sync(void);
+void *exags_host_malloc_pinned(size_t bytes);
+void  exags_host_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,135 @@
+"""One rank of a multi-process test.  Launched by the tests with RANK /
+WORLD_SIZE / MASTER_ADDR / MASTER_PORT / EXAGS_JOB_KEY set; ranks talk to each
+other through torch.distributed (gloo on CPU, nccl not needed) for the test's
+own bookkeeping, while the library under test uses its own host rendezvous
+(and NCCL on GPUs).  Rank 0 checks everything against the oracle and exits
+non-zero on any mismatch."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [os.path.join(ROOT, "exaflow-exags-upc_b200"), os.path.join(ROOT, "oracle"), HERE]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import cases  # noqa: E402
+
+
+def make_ids(case, np_, rank):
+    from exags_b200 import semmesh
+    if case == "fixture":
+        return cases.gs_test_fixture_ids(np_, rank)
+    if case == "slab":
+        return semmesh.box_ids(3, 3, 2, 3, ez0=2 * rank, Ez_global=2 * np_)
+    if case == "blocks":
+        return semmesh.block_partition_ids(4, 4, 4, 2, 2, 2, 2, np_, rank)[0]
+    if case == "random":
+        return cases.random_ids(700 + 31 * rank, 300, 99 + rank)
+    if case == "empty":      # rank 1 owns nothing
+        return cases.random_ids(0 if rank == 1 else 200, 80, 5 + rank)
+    raise SystemExit(f"unknown case {case}")
+
+
+def gather_arrays(a, np_):
+    """all ranks -> list of numpy arrays on every rank (gloo)."""
+    out = [None] * np_
+    dist.all_gather_object(out, a)
+    return out
+
+
+def main():
+    case, what = sys.argv[1], sys.argv[2]
+    unique = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    method = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    rank, np_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    gpu = what == "exec"
+    if not gpu:
+        os.environ["EXAGS_HOST_SETUP_ONLY"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=np_)
+    import exags_b200 as X
+    import oracle as O
+    if gpu:
+        ndev = torch.cuda.device_count()
+        X.lib().exags_set_device(rank % ndev)
+    ids = make_ids(case, np_, rank)
+    g = X.gs_setup(ids, unique=unique, method=method)
+    info = g.info()
+    all_ids = gather_arrays(ids, np_)
+    ok = True
+    orc = O.Oracle(all_ids, unique=unique,
+                   method=O.METHOD_ALLREDUCE if method == 3 else O.METHOD_PAIRWISE) if rank == 0 else None
+
+    if what == "setup":
+        dumps = gather_arrays([g.dump_map(w) for w in range(5)], np_)
+        infos = gather_arrays(info, np_)
+        if rank == 0:
+            for r in range(np_):
+                for w in range(5):
+                    want = orc.map(r, w)
+                    if not np.array_equal(dumps[r][w], want):
+                        print(f"MISMATCH case={case} rank={r} map={w}\n got {dumps[r][w][:40]}\n want {want[:40]}")
+                        ok = False
+                if infos[r]["total_shared"] != orc.total_shared:
+                    print(f"MISMATCH total_shared rank={r}: {infos[r]['total_shared']} vs {orc.total_shared}")
+                    ok = False
+    elif what == "unique":
+        mine = ids.copy()
+        X.gs_unique(mine)
+        got = gather_arrays(mine, np_)
+        if rank == 0:
+            want = [a.copy() for a in all_ids]
+            O.unique(want)
+            for r in range(np_):
+                if not np.array_equal(got[r], want[r]):
+                    print(f"MISMATCH gs_unique rank={r}\n got {got[r][:40]}\n want {want[r][:40]}")
+                    ok = False
+    elif what == "exec":
+        import itertools
+        combos = list(itertools.product(cases.DTYPES.items(), cases.OPS, (0, 1), (0, 1, 2)))
+        for (dname, dt), op, t, mode in combos:
+            vn = 1 if mode == 0 else 3
+            opi = cases.OPS.index(op)
+            dom = X.NP_DOM[np.dtype(dt)]
+            if mode == 2:
+                u = [cases.values(ids.size, dt, op, 1000 * rank + k) for k in range(vn)]
+                dev = [torch.from_numpy(x.copy()).cuda() for x in u]
+                X.gs_many(dev, vn, dom, opi, t, g)
+                got = [d.cpu().numpy() for d in dev]
+            else:
+                u = cases.values(ids.size * vn, dt, op, 1000 * rank + 7)
+                dev = torch.from_numpy(u.copy()).cuda()
+                (X.gs if mode == 0 else lambda *a: X.gs_vec(a[0], vn, *a[1:]))(dev, dom, opi, t, g)
+                got = dev.cpu().numpy()
+            ins = gather_arrays(u, np_)
+            outs = gather_arrays(got, np_)
+            if rank == 0:
+                want = [[x.copy() for x in a] if mode == 2 else a.copy() for a in ins]
+                orc.exec(want, mode, vn, O.NP_DOM[np.dtype(dt)], opi, t)
+                for r in range(np_):
+                    w = np.stack(want[r]) if mode == 2 else want[r]
+                    gg = np.stack(outs[r]) if mode == 2 else outs[r]
+                    exact = np.array_equal(gg, w)
+                    if not exact and np.dtype(dt).kind == "f" and op in ("add", "mul") and method == 3:
+                        try:
+                            np.testing.assert_array_max_ulp(gg, w, maxulp=4)
+                            exact = True
+                        except AssertionError:
+                            pass
+                    if not exact:
+                        bad = np.flatnonzero(gg.ravel() != w.ravel())
+                        print(f"MISMATCH exec case={case} {dname} {op} t={t} mode={mode} rank={r}: "
+                              f"{bad.size} of {w.size} differ, first at {bad[:5]}")
+                        ok = False
+    flag = torch.tensor([0 if ok else 1])
+    dist.broadcast(flag, 0)
+    X.gs_free(g)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(flag.item()))
+
+
+if __name__ == "__main__":
+    main()

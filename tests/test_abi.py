@@ -1,0 +1,67 @@
+"""The C-ABI library loads and exports every function include/*.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = set()
+    for h in ("exags.h", "exags_cuda.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+        for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src):
+            n = m.group(1)
+            if n.startswith(("exags_", "gslib_", "fgslib_")):
+                names.add(n)
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(X):
+    L = ctypes.CDLL(X.LIB_PATH)
+    names = declared_functions()
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_fortran_and_data_symbols(X):
+    L = ctypes.CDLL(X.LIB_PATH)
+    for n in ("gs_setup_", "gs_op_", "gs_op_vec_", "gs_op_many_", "gs_op_fields_", "gs_free_",
+              "gs_setup_pick_", "gs_op", "gs_op_vec", "gs_op_many", "gs_op_fields",
+              "exags_glb_comm", "exags_comm_gbl_id", "exags_comm_gbl_np"):
+        assert hasattr(L, n), n
+
+
+def test_compat_headers_compile(tmp_path):
+    """A caller written against the reference's header names compiles."""
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdlib.h>
+#include "exags/c99.h"
+#include "exags/name.h"
+#include "exags/fail.h"
+#include "exags/types.h"
+#include "exags/comm.h"
+#include "exags/mem.h"
+#include "exags/gs_defs.h"
+#include "exags/gs.h"
+int caller(void) {
+  comm_ptr cp; struct gs_data *gsh; buffer b = null_buffer;
+  comm_init(); comm_world(&cp);
+  slong *id = tmalloc(slong, 4); double v[4] = {1,1,1,1};
+  id[0]=1; id[1]=1; id[2]=2; id[3]=0;
+  gsh = gs_setup(id, 4, cp, 0, gs_pairwise, 0); free(id);
+  gs(v, gs_double, gs_add, 0, gsh, &b);
+  gs_free(gsh); comm_free(&cp);
+  return (int)cp->np;
+}''')
+    import subprocess
+    for flags in ([], ["-DGLOBAL_LONG_LONG"]):
+        r = subprocess.run(["gcc", "-std=gnu99", "-c", str(src), "-I", os.path.join(ROOT, "include"),
+                            "-o", str(tmp_path / "caller.o")] + flags, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

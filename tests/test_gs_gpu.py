@@ -1,0 +1,289 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI.
+Bit-exact for every domain and op (one thread reduces a group left to right
+in the reference's order, so even float/double add/mul agree exactly; the
+north star allows 4 ulp there)."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+import cases
+from exags_b200 import semmesh
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).copy()).cuda()
+
+
+def _run_both(X, O, g, o, dt, op, t, mode, vn, n, seed, host=False):
+    opi = cases.OPS.index(op)
+    dom, odom = X.NP_DOM[np.dtype(dt)], O.NP_DOM[np.dtype(dt)]
+    if mode == 2:
+        u = [cases.values(n, dt, op, seed + k) for k in range(vn)]
+        want = [x.copy() for x in u]
+        o.exec([want], O.M_MANY, vn, odom, opi, t)
+        if host:
+            got = [x.copy() for x in u]
+            X.gs_many(got, vn, dom, opi, t, g)
+        else:
+            d = [_dev(x) for x in u]
+            X.gs_many(d, vn, dom, opi, t, g)
+            got = [x.cpu().numpy() for x in d]
+        return np.stack(got), np.stack(want)
+    u = cases.values(n * vn, dt, op, seed)
+    want = u.copy()
+    o.exec([want], mode, vn, odom, opi, t)
+    if host:
+        got = u.copy()
+        (X.gs(got, dom, opi, t, g) if mode == 0 else X.gs_vec(got, vn, dom, opi, t, g))
+    else:
+        d = _dev(u)
+        (X.gs(d, dom, opi, t, g) if mode == 0 else X.gs_vec(d, vn, dom, opi, t, g))
+        got = d.cpu().numpy()
+    return got, want
+
+
+def test_known_answers_on_gpu(X):
+    """outputs of the reference for a flagged label set."""
+    g = X.gs_setup(cases.known_answer_ids())
+    for t, want in ((0, [0, 12, 12, 12, 12, 14, 17, 14, 17, 17, 11, 12, 12, 12, 15, 15]),
+                    (1, [1, 2, 14, 14, 14, 14, 26, 14, 9, 26, 11, 39, 13, 14, 31, 16])):
+        d = _dev(np.arange(1, 17, dtype=np.float64))
+        X.gs(d, X.gs_double, X.gs_add, t, g)
+        assert d.cpu().numpy().tolist() == want
+    h = np.arange(1, 17, dtype=np.float64)
+    X.gs(h, X.gs_double, X.gs_max, 0, g)
+    assert h.tolist() == [-np.finfo(np.float64).max, 5, 5, 5, 5, 8, 10, 8, 10, 10, 11, 12, 12, 12, 15, 15]
+    X.gs_free(g)
+
+
+def test_reference_fixture_np1(X):
+    """tests/gs/gs_test.upc:138-144 at np=1."""
+    g = X.gs_setup(cases.gs_test_fixture_ids(1, 0))
+    for t, want in ((0, 3.0), (1, 4.0)):
+        v = np.ones(5)
+        X.gs(v, X.gs_double, X.gs_add, t, g)
+        assert v[4] == want
+    X.gs_free(g)
+
+
+@pytest.mark.parametrize("dname,op", list(itertools.product(cases.DTYPES, cases.OPS)))
+def test_all_domains_ops_flagged(X, O, dname, op):
+    """every gs_dom x gs_op, transpose 0/1, plain/vec/many, on labels with
+    zeros, flags, singletons and one 40-member group."""
+    dt = cases.DTYPES[dname]
+    ids = cases.random_ids(6000, 1500, 42, long_group=40)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for t, (mode, vn) in itertools.product((0, 1), ((0, 1), (1, 3), (2, 3), (1, 5), (2, 11))):
+        got, want = _run_both(X, O, g, o, dt, op, t, mode, vn, ids.size, 7 * vn + t)
+        assert np.array_equal(got, want), (dname, op, t, mode, vn)
+    X.gs_free(g)
+
+
+def test_host_pointers_staged(X, O):
+    ids = cases.random_ids(3000, 700, 5)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for mode, vn in ((0, 1), (1, 3), (2, 3)):
+        got, want = _run_both(X, O, g, o, np.float64, "add", 0, mode, vn, ids.size, 3, host=True)
+        assert np.array_equal(got, want)
+    X.gs_free(g)
+
+
+def test_bpr_integer(X, O):
+    ids = cases.random_ids(2000, 300, 9, p_flag=0.0)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    u = np.random.default_rng(1).integers(0, 1 << 20, size=ids.size).astype(np.int32)
+    want = u.copy()
+    o.exec([want], O.M_PLAIN, 1, O.D_INT, O.O_BPR, 0)
+    d = _dev(u)
+    X.gs(d, X.gs_int, X.gs_bpr, 0, g)
+    assert np.array_equal(d.cpu().numpy(), want)
+    X.gs_free(g)
+
+
+@pytest.mark.parametrize("ids", [np.zeros(0, np.int64), np.zeros(5, np.int64), np.array([-7], np.int64),
+                                 np.arange(1, 50, dtype=np.int64)], ids=["empty", "allzero", "singleflag", "nogroups"])
+def test_degenerate_inputs(X, O, ids):
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for t in (0, 1):
+        u = np.arange(1, ids.size + 1, dtype=np.float64)
+        want = u.copy()
+        o.exec([want], O.M_PLAIN, 1, O.D_DOUBLE, O.O_ADD, t)
+        got = u.copy()
+        if ids.size:
+            X.gs(got, X.gs_double, X.gs_add, t, g)
+        assert np.array_equal(got, want)
+    X.gs_free(g)
+
+
+def test_config1_small_sem_mesh(X, O):
+    """BASELINE config 1: 2x2x2 hex N=3, add/min/max on double and int."""
+    ids = semmesh.box_ids(2, 2, 2, 3)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    v = _dev(np.ones(512))
+    X.gs(v, X.gs_double, X.gs_add, 0, g)
+    v = v.cpu().numpy()
+    assert v.sum() == 1000 and v.max() == 8
+    for dt, op in itertools.product((np.float64, np.int32), ("add", "min", "max")):
+        got, want = _run_both(X, O, g, o, dt, op, 0, 0, 1, 512, 1)
+        assert np.array_equal(got, want)
+    iv = _dev(np.arange(512, dtype=np.int32))
+    X.gs(iv, X.gs_int, X.gs_max, 0, g)
+    assert int(iv[3]) == 64
+    X.gs_free(g)
+
+
+def test_unique_handle(X, O):
+    ids = cases.random_ids(4000, 900, 13, p_flag=0.0)
+    g, o = X.gs_setup(ids, unique=1), O.Oracle([ids], unique=1)
+    for t in (0, 1):
+        got, want = _run_both(X, O, g, o, np.float64, "add", t, 0, 1, ids.size, t)
+        assert np.array_equal(got, want)
+    X.gs_free(g)
+
+
+def test_config3_vec_many_n7(X, O):
+    """BASELINE config 3 shape: N=7 box, 3 components, float and double."""
+    dims = (6, 5, 4, 7)
+    ids = semmesh.box_ids(*dims)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for dt, (mode, vn) in itertools.product((np.float32, np.float64), ((1, 3), (2, 3))):
+        got, want = _run_both(X, O, g, o, dt, "add", 0, mode, vn, ids.size, 17)
+        assert np.array_equal(got, want)
+    X.gs_free(g)
+
+
+def test_medium_mesh_vs_oracle(X, O):
+    """16x16x8 N=7 (1.05 M DOF): the largest size the oracle sets up in seconds."""
+    dims = (16, 16, 8, 7)
+    ids = semmesh.box_ids(*dims)
+    dof = semmesh.slab_dof_numbers(*dims)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for dt, op in ((np.float64, "add"), (np.float32, "mul"), (np.int64, "min"), (np.int32, "max")):
+        u = semmesh.field_values(dof, dt, op)
+        want = u.copy()
+        o.exec([want], O.M_PLAIN, 1, O.NP_DOM[np.dtype(dt)], cases.OPS.index(op), 0)
+        d = _dev(u)
+        X.gs(d, X.NP_DOM[np.dtype(dt)], cases.OPS.index(op), 0, g)
+        assert np.array_equal(d.cpu().numpy(), want)
+    X.gs_free(g)
+
+
+def test_full_size_properties(X):
+    """BASELINE config 2 at full size (M7, 100 663 296 DOF): size-independent
+    properties.  gs(add) of ones is the multiplicity m; sum(1/m) counts the
+    unique nodes (exact: m is a power of two); gs(max) is idempotent; gs(add)
+    is linear under exact scalings; the field is symmetric afterwards."""
+    dims = (64, 64, 48, 7)
+    c = semmesh.box_counts(*dims)
+    ids = semmesh.box_ids(*dims)
+    g = X.gs_setup(ids)
+    info = g.info()
+    assert (info["n"], info["groups"], info["members"]) == (c["n"], c["groups"], c["members"])
+    assert info["sectors_f64"] == c["n"] // 4        # every 32 B sector is touched at N=7
+    idt = torch.from_numpy(ids).cuda()
+    del ids
+    m = torch.ones(c["n"], dtype=torch.float64, device="cuda")
+    X.gs(m, X.gs_double, X.gs_add, 0, g)
+    assert set(torch.unique(m).tolist()) == {1.0, 2.0, 4.0, 8.0}
+    assert float((1.0 / m).sum()) == float(c["unique"])
+    # every copy of a node holds the same value after gs: compare with a
+    # scatter-reduce by global id done by torch on the same GPU
+    x = torch.rand(c["n"], dtype=torch.float64, device="cuda") + 0.5
+    y = x.clone()
+    X.gs(y, X.gs_double, X.gs_max, 0, g)
+    ref = torch.full((c["unique"] + 1,), -1.0, dtype=torch.float64, device="cuda")
+    ref.scatter_reduce_(0, idt, x, reduce="amax")
+    assert torch.equal(y, ref[idt])
+    y2 = y.clone()
+    X.gs(y2, X.gs_double, X.gs_max, 0, g)
+    assert torch.equal(y, y2)                          # idempotent
+    a = x.clone(); X.gs(a, X.gs_double, X.gs_add, 0, g)
+    b = (4.0 * x); X.gs(b, X.gs_double, X.gs_add, 0, g)
+    assert torch.equal(b, 4.0 * a)                     # linear under exact scaling
+    iv = torch.randint(-1000, 1001, (c["n"],), dtype=torch.int64, device="cuda")
+    want = torch.zeros(c["unique"] + 1, dtype=torch.int64, device="cuda").scatter_add_(0, idt, iv)[idt]
+    X.gs(iv, X.gs_long, X.gs_add, 0, g)
+    assert torch.equal(iv, want)                       # integer add is exact
+    X.gs_free(g)
+
+
+def test_fortran_bindings(X):
+    """fgs_setup / gs_op / gs_op_vec / gs_op_many / gs_op_fields / gs_free by reference
+    (src/gs.upc:1309-1418), Nek flavour: dom 1..3, op 1..4, 0-based handles."""
+    L = X.lib()
+    ids = cases.random_ids(500, 100, 3, p_flag=0.0)
+    n = C.c_int(ids.size); h = C.c_int(-1); zero = C.c_int(0)
+    L.fgslib_gs_setup_(C.byref(h), ids.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(zero), C.byref(zero))
+    assert h.value >= 0
+    g = X.gs_setup(ids)
+    i = lambda v: C.byref(C.c_int(v))
+    u = cases.values(ids.size, np.float64, "add", 1); want = u.copy()
+    X.gs(want, X.gs_double, X.gs_add, 0, g)
+    L.fgslib_gs_op_(C.byref(h), u.ctypes.data_as(C.c_void_p), i(1), i(1), i(0))
+    assert np.array_equal(u, want)
+    u = cases.values(ids.size, np.int64, "max", 2); want = u.copy()
+    X.gs(want, X.gs_long, X.gs_max, 0, g)
+    L.fgslib_gs_op_(C.byref(h), u.ctypes.data_as(C.c_void_p), i(3), i(4), i(0))
+    assert np.array_equal(u, want)
+    u = cases.values(ids.size * 2, np.float64, "add", 3); want = u.copy()
+    X.gs_vec(want, 2, X.gs_double, X.gs_add, 1, g)
+    L.fgslib_gs_op_vec_(C.byref(h), u.ctypes.data_as(C.c_void_p), i(2), i(1), i(1), i(1))
+    assert np.array_equal(u, want)
+    f = cases.values(ids.size * 3, np.float64, "add", 4); want = f.copy()
+    X.gs_many([want[k * ids.size:(k + 1) * ids.size] for k in range(3)], 3, X.gs_double, X.gs_add, 0, g)
+    L.fgslib_gs_op_fields_(C.byref(h), f.ctypes.data_as(C.c_void_p), i(ids.size), i(3), i(1), i(1), i(0))
+    assert np.array_equal(f, want)
+    L.fgslib_gs_free_(C.byref(h))
+    X.gs_free(g)
+
+
+def test_gs_local_api(X):
+    """Public gs_local.h kernels on sentinel maps (src/gs_local.h:23-41) against
+    a plain Python statement of src/gs_local.c:60-97."""
+    NIL = 0xFFFFFFFF
+    mp = np.array([2, 3, 4, 1, NIL, 5, 7, NIL, 6, 9, 8, NIL, NIL], dtype=np.uint32)
+    u = np.arange(1, 13, dtype=np.float64)
+    want = u.copy()
+    for grp in ([2, 3, 4, 1], [5, 7], [6, 9, 8]):
+        for j in grp[1:]:
+            want[grp[0]] += u[j]
+    got = u.copy()
+    X.lib().exags_gs_gather(got.ctypes.data, got.ctypes.data, 1, mp.ctypes.data, X.gs_double, X.gs_add)
+    assert np.array_equal(got, want)
+    want2 = want.copy()
+    for grp in ([2, 3, 4, 1], [5, 7], [6, 9, 8]):
+        for j in grp[1:]:
+            want2[j] = want2[grp[0]]
+    X.lib().exags_gs_scatter(got.ctypes.data, got.ctypes.data, 1, mp.ctypes.data, X.gs_double)
+    assert np.array_equal(got, want2)
+    lst = np.array([0, 5, NIL], dtype=np.uint32)
+    X.lib().exags_gs_init(got.ctypes.data, 1, lst.ctypes.data, X.gs_double, X.gs_min)
+    assert got[0] == np.finfo(np.float64).max and got[5] == np.finfo(np.float64).max
+    a, b = np.arange(6, dtype=np.int32), np.arange(6, dtype=np.int32)[::-1].copy()
+    X.lib().exags_gs_gather_array(a.ctypes.data, b.ctypes.data, 6, X.gs_int, X.gs_max)
+    assert a.tolist() == [5, 4, 3, 3, 4, 5]
+    X.lib().exags_gs_init_array(a.ctypes.data, 6, X.gs_int, X.gs_mul)
+    assert a.tolist() == [1] * 6
+    # many -> vec pack and vec -> many unpack (pairwise buffer layout [slot][vn])
+    pm = np.array([3, 0, NIL, 5, 1, NIL, NIL], dtype=np.uint32)     # u[3]->buf[0], u[5]->buf[1]
+    us = [np.arange(10, 16, dtype=np.float64) + 100 * k for k in range(2)]
+    tab = (C.c_void_p * 2)(*[x.ctypes.data for x in us])
+    buf = np.zeros(4)
+    X.lib().exags_gs_scatter_many_to_vec(buf.ctypes.data, C.addressof(tab), 2, pm.ctypes.data, X.gs_double)
+    assert buf.tolist() == [13, 113, 15, 115]
+    X.lib().exags_gs_gather_vec_to_many(C.addressof(tab), buf.ctypes.data, 2, pm.ctypes.data, X.gs_double, X.gs_add)
+    assert us[0][3] == 26 and us[1][3] == 226 and us[0][5] == 30 and us[1][5] == 230
+
+
+def test_kernels_really_launch(X):
+    ids = cases.random_ids(1000, 200, 1)
+    g = X.gs_setup(ids)
+    before = X.kernel_launches()
+    X.gs(_dev(np.ones(ids.size)), X.gs_double, X.gs_add, 0, g)
+    assert X.kernel_launches() > before
+    X.gs_free(g)

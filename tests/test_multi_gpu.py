@@ -1,0 +1,32 @@
+"""Multi-rank parity on real GPUs: one process per GPU, NCCL halo exchange,
+every domain x op x transpose x mode against the oracle (rank 0 checks).
+Needs at least 2 devices; the 1-GPU box skips these and relies on the CPU
+multi-rank setup tests plus the single-device exchange test below."""
+import pytest
+
+from mp_launch import run_ranks
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _ndev():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("np_,case,method", [(2, "slab", 1), (2, "fixture", 1), (2, "random", 1),
+                                             (2, "slab", 3), (2, "empty", 1), (4, "blocks", 1),
+                                             (4, "blocks", 3), (8, "blocks", 1)])
+def test_multirank_exec_nccl(built, np_, case, method):
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "exec", 0, method], timeout=600)
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
+def test_multirank_exec_unique(built, np_, case):
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "exec", 1, 1], timeout=600)
+    assert all(c == 0 for c in codes), "\n".join(outs)

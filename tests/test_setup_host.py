@@ -1,0 +1,81 @@
+"""Host-side gs_setup logic against the oracle, without a GPU: local maps at
+np=1 and, through 2..4 real processes (gloo for the test's bookkeeping, the
+library's own shared-memory rendezvous for its id exchange), the shared-label
+discovery, pairwise maps and gs_unique."""
+import numpy as np
+import pytest
+
+import cases
+from exags_b200 import semmesh
+from mp_launch import run_ranks
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_local_maps_random(X, O, seed):
+    ids = cases.random_ids(2000 + 137 * seed, 500, seed, long_group=40 if seed % 2 else 0)
+    g = X.gs_setup(ids)
+    o = O.Oracle([ids])
+    for w in (0, 1, 2):
+        assert np.array_equal(g.dump_map(w), o.map(0, w)), w
+    X.gs_free(g)
+
+
+@pytest.mark.parametrize("ids", [np.zeros(0, np.int64), np.zeros(5, np.int64),
+                                 np.array([7], np.int64), np.array([-7], np.int64),
+                                 np.arange(1, 50, dtype=np.int64)],
+                         ids=["empty", "allzero", "single", "singleflag", "nogroups"])
+def test_local_maps_degenerate(X, O, ids):
+    g = X.gs_setup(ids)
+    o = O.Oracle([ids])
+    for w in (0, 1, 2):
+        assert np.array_equal(g.dump_map(w), o.map(0, w)), w
+    X.gs_free(g)
+
+
+def test_int32_flavour_matches_int64(X):
+    ids = cases.random_ids(900, 200, 3)
+    a, b = X.gs_setup(ids), X.gs_setup(ids.astype(np.int32))
+    for w in (0, 1, 2):
+        assert np.array_equal(a.dump_map(w), b.dump_map(w))
+    X.gs_free(a); X.gs_free(b)
+
+
+def test_sem_mesh_counts(X):
+    """Group/member counts of a box match the closed forms of SURVEY.md 8."""
+    dims = (5, 4, 3, 4)
+    g = X.gs_setup(semmesh.box_ids(*dims))
+    c = semmesh.box_counts(*dims)
+    info = g.info()
+    assert (info["n"], info["groups"], info["members"]) == (c["n"], c["groups"], c["members"])
+    X.gs_free(g)
+
+
+def test_unique_np1(X, O):
+    ids = cases.random_ids(1500, 300, 11, p_flag=0.0)
+    mine, want = ids.copy(), [ids.copy()]
+    X.gs_unique(mine)
+    O.unique(want)
+    assert np.array_equal(mine, want[0])
+    g, o = X.gs_setup(ids, unique=1), O.Oracle([ids], unique=1)
+    for w in (0, 1, 2):
+        assert np.array_equal(g.dump_map(w), o.map(0, w)), w
+    X.gs_free(g)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "fixture"), (2, "slab"), (3, "random"), (4, "blocks"),
+                                      (2, "empty"), (4, "fixture")])
+def test_multirank_setup(built, np_, case):
+    codes, outs = run_ranks(np_, [case, "setup"])
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (3, "blocks")])
+def test_multirank_setup_unique(built, np_, case):
+    codes, outs = run_ranks(np_, [case, "setup", 1])
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (3, "random"), (4, "blocks")])
+def test_multirank_gs_unique(built, np_, case):
+    codes, outs = run_ranks(np_, [case, "unique"])
+    assert all(c == 0 for c in codes), "\n".join(outs)
