@@ -82,6 +82,28 @@ struct xg_hmap {
   u32 *nunf;          /* [ng] unflagged members per group (NULL: all unflagged) */
 };
 void xg_hmap_free(struct xg_hmap *m);
+
+/* Sliced-ELL view of a symmetric CSR map (after SELL-C-sigma, Kreutzer et
+   al. 2014, C = 32).  Groups are stably sorted by size class inside windows of
+   `sigma` consecutive groups (so neighbours in the field stay neighbours), and
+   packed into fixed-size blocks of 32 lanes x 8 member slots = 256 indices
+   (1 KB): a block of class W holds 8/W sub-chunks of 32 groups, lane l of
+   sub-chunk s owning slots [s*W, s*W+W) of its 8.  Each lane's 8 slots are
+   contiguous, so a warp reads a block with two coalesced 128-bit loads per
+   lane and then has 8 independent field loads in flight per lane whatever the
+   group size.  No per-group offsets remain; one class byte per block.
+   Unused slots hold XG_NONE.  Groups with more than 8 members stay in a
+   residual CSR.                                                             */
+#define XG_SELL_WMAX 8
+struct xg_sell {
+  u32  nblock;        /* blocks of 256 indices                               */
+  unsigned char *cls; /* [nblock] 2, 4 or 8                                  */
+  u32 *idx;           /* [nblock*256]                                        */
+  size_t nidx;
+  struct xg_hmap rest;/* groups with more than XG_SELL_WMAX members          */
+};
+void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m, u32 sigma);
+void xg_sell_free(struct xg_sell *s);
 void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m);
 u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *count);
 
@@ -142,6 +164,15 @@ struct xcu_csr {
   u32 ng, ni;
   const u32 *off, *idx, *nunf;   /* device pointers; nunf may be NULL */
 };
+
+/* device SELL map */
+struct xcu_sell {
+  u32 nblock;
+  const unsigned char *cls;
+  const u32 *idx;
+};
+void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
+                    int mode, int xdom, int xop);
 
 /* boundary description on the device (np>1) */
 struct xcu_bnd {

@@ -35,7 +35,11 @@ struct gs_data {
   struct xg_plan plan;        /* np > 1 */
   u64 sectors_f64;            /* distinct 32-byte sectors of a double field touched */
   /* device */
-  struct dev_csr d_int;       /* interior groups (all groups when np == 1) */
+  struct dev_csr d_int;       /* interior groups (all groups when np == 1): CSR form,
+                                 or only the long-group residue when d_sell is used */
+  struct xcu_sell d_sell;     /* interior groups, sliced-ELL form (symmetric maps) */
+  void *d_sell_mem[2];
+  size_t sell_idx_entries;
   u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
   struct xcu_bnd d_bnd;       /* boundary primaries */
   void *d_bnd_mem[10];
@@ -150,6 +154,7 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
     f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = 0;
     if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
     else f.p[0] = ptrs[0];
+    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
@@ -180,7 +185,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   if (vn == 0) return;
   transpose = transpose != 0;
   struct xg_world *w = g->w;
-  if (!stream) stream = xg_world_stream(w, 0);
+  if (blocking) stream = xg_world_stream(w, 0);   /* async callers own `stream` (0 = legacy default) */
   const size_t esz = xg_dom_bytes(xd), n = g->n;
 
   void **ptrs = xnew(void *, vn);
@@ -295,8 +300,24 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     bgoff[nb] = (u32)ob;
   }
   g->nfs = (u32)nfs;
+  /* symmetric maps take the sliced-ELL layout (EXAGS_LAYOUT=csr keeps CSR) */
+  struct xg_sell sell; memset(&sell, 0, sizeof sell);
+  const char *lay = getenv("EXAGS_LAYOUT");
+  int use_sell = !in.nunf && in.ng && !(lay && strcmp(lay, "csr") == 0);
+  if (use_sell) {
+    const char *tg = getenv("EXAGS_SELL_SIGMA");
+    xg_sell_build(&sell, &in, tg && atoi(tg) > 0 ? (u32)atoi(tg) : 8192u);
+    g->sell_idx_entries = sell.nidx;
+  }
+  if (g->on_device && use_sell) {
+    upload_csr(&g->d_int, &sell.rest);
+    g->d_sell.nblock = sell.nblock;
+    g->d_sell_mem[0] = upload(sell.cls, (size_t)(sell.nblock ? sell.nblock : 1));
+    g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
+    g->d_sell.cls = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
+  }
   if (g->on_device) {
-    upload_csr(&g->d_int, &in);
+    if (!use_sell) upload_csr(&g->d_int, &in);
     if (nfs) g->d_fs = (u32 *)upload(fs, nfs * sizeof(u32));
     if (nb) {
       int m = 0;
@@ -319,6 +340,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     g->d_int.c.ng = in.ng; g->d_int.c.ni = in.ni;
   }
   g->handle_bytes += ((size_t)ng + 1 + ni + nfs + nb + 1 + bni + nb) * sizeof(u32);
+  xg_sell_free(&sell);
   xg_hmap_free(&in); free(fs); free(bgoff); free(bgidx); free(bnunf);
 }
 
@@ -462,6 +484,7 @@ void exags_gs_free(struct gs_data *g)
     xcu_device_sync();
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
     xcu_free(g->d_fs);
+    for (int m = 0; m < 2; ++m) xcu_free(g->d_sell_mem[m]);
     for (int m = 0; m < 10; ++m) xcu_free(g->d_bnd_mem[m]);
   }
   xg_hmap_free(&g->hall);
@@ -510,6 +533,7 @@ void exags_gs_info(const struct gs_data *g, unsigned long long what[16])
   what[7] = g->plan.total_shared; what[8] = (unsigned long long)g->method;
   what[9] = g->sectors_f64; what[10] = g->plan.nb; what[11] = g->d_int.c.ng;
   what[12] = g->d_int.c.ni; what[13] = g->nfs; what[14] = g->handle_bytes;
+  what[15] = g->sell_idx_entries;
 }
 
 size_t exags_gs_dump_map(const struct gs_data *g, int which, exags_uint *out, size_t cap)

@@ -170,3 +170,86 @@ u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *c
   *count = (u32)c;
   return out;
 }
+
+/* ------------------------------------------------------------------ */
+void xg_sell_free(struct xg_sell *s)
+{
+  free(s->cls); free(s->idx);
+  xg_hmap_free(&s->rest);
+  memset(s, 0, sizeof *s);
+}
+
+static inline int sell_class(u32 size) { return size <= 2 ? 0 : size <= 4 ? 1 : 2; }
+
+void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m, u32 sigma)
+{
+  static const u32 W[3] = { 2, 4, 8 }, GPB[3] = { 128, 64, 32 };   /* groups per block */
+  memset(s, 0, sizeof *s);
+  if (sigma < 128) sigma = 128;
+  /* long groups go to the residual CSR */
+  size_t nlong = 0, ilong = 0, nshort = 0;
+  for (u32 g = 0; g < m->ng; ++g) {
+    u32 sz = m->off[g + 1] - m->off[g];
+    if (sz > XG_SELL_WMAX) { ++nlong; ilong += sz; } else ++nshort;
+  }
+  s->rest.ng = (u32)nlong; s->rest.ni = (u32)ilong;
+  s->rest.off = xnew(u32, nlong + 1);
+  s->rest.idx = xnew(u32, ilong ? ilong : 1);
+  u32 *sg = xnew(u32, nshort ? nshort : 1);        /* short groups, primary order */
+  {
+    size_t og = 0, oi = 0, os = 0;
+    for (u32 g = 0; g < m->ng; ++g) {
+      u32 a = m->off[g], sz = m->off[g + 1] - a;
+      if (sz > XG_SELL_WMAX) {
+        s->rest.off[og++] = (u32)oi;
+        memcpy(s->rest.idx + oi, m->idx + a, (size_t)sz * sizeof(u32));
+        oi += sz;
+      } else sg[os++] = g;
+    }
+    s->rest.off[nlong] = (u32)oi;
+  }
+  size_t nwin = (nshort + sigma - 1) / sigma;
+  /* pass 1: blocks per window */
+  u32 *wstart = xnew(u32, nwin + 1);
+  size_t nblock = 0;
+  for (size_t w = 0; w < nwin; ++w) {
+    size_t g0 = w * sigma, g1 = g0 + sigma < nshort ? g0 + sigma : nshort;
+    u32 cnt[3] = { 0, 0, 0 };
+    for (size_t k = g0; k < g1; ++k) ++cnt[sell_class(m->off[sg[k] + 1] - m->off[sg[k]])];
+    wstart[w] = (u32)nblock;
+    for (int c = 0; c < 3; ++c) nblock += (cnt[c] + GPB[c] - 1) / GPB[c];
+  }
+  wstart[nwin] = (u32)nblock;
+  if (nblock >> 23) xfail("gs_setup: map too large for the sliced layout");
+  s->nblock = (u32)nblock;
+  s->nidx = nblock * 256;
+  s->cls = xnew(unsigned char, nblock ? nblock : 1);
+  s->idx = xnew(u32, s->nidx ? s->nidx : 1);
+  /* pass 2: fill, windows are independent */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+  for (size_t w = 0; w < nwin; ++w) {
+    size_t g0 = w * sigma, g1 = g0 + sigma < nshort ? g0 + sigma : nshort;
+    size_t blk = wstart[w];
+    for (int c = 0; c < 3; ++c) {
+      size_t in_class = 0;
+      u32 *base = 0;
+      for (size_t k = g0; k < g1; ++k) {
+        u32 g = sg[k], a = m->off[g], sz = m->off[g + 1] - a;
+        if (sell_class(sz) != c) continue;
+        size_t j = in_class % GPB[c];
+        if (j == 0) {                       /* open a new block */
+          base = s->idx + blk * 256;
+          for (int z = 0; z < 256; ++z) base[z] = XG_NONE;
+          s->cls[blk] = (unsigned char)W[c];
+          ++blk;
+        }
+        u32 lane = (u32)(j & 31u), sub = (u32)(j >> 5);
+        for (u32 q = 0; q < sz; ++q) base[lane * 8 + sub * W[c] + q] = m->idx[a + q];
+        ++in_class;
+      }
+    }
+  }
+  free(wstart); free(sg);
+}

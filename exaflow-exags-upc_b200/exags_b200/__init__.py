@@ -157,7 +157,8 @@ class GS:
         lib().exags_gs_info(self.ptr, a)
         keys = ["n", "groups", "members", "flagged_primaries", "neighbours", "send_slots",
                 "recv_slots", "total_shared", "method", "sectors_f64", "boundary",
-                "interior_groups", "interior_members", "flagged_singles", "handle_bytes"]
+                "interior_groups", "interior_members", "flagged_singles", "handle_bytes",
+                "sell_entries"]
         return {k: int(a[i]) for i, k in enumerate(keys)}
 
     def dump_map(self, which: int) -> np.ndarray:

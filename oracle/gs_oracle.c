@@ -496,7 +496,11 @@ void ogs_exec(ogs *h, void *const *u, int mode, unsigned vn, int dom, int op, in
   struct view *v = zalloc((size_t)np * sizeof *v);
   for (int p = 0; p < np; ++p) make_view(&v[p], u[p], mode, vn, dom);
 
-  /* local gather + init (gs.upc:1181-1182) */
+  /* local gather + init (gs.upc:1181-1182).  Ranks are the reference's SPMD
+     threads: each phase runs them side by side on the host cores (OpenMP),
+     with the implicit barrier between phases standing in for the put/flag
+     handshake of pw_exec_sends/recvs. */
+#pragma omp parallel for schedule(static)
   for (int p = 0; p < np; ++p) {
     struct rank_data *r = &h->r[p];
     for (unsigned k = 0; k < nv; ++k) {
@@ -509,12 +513,14 @@ void ogs_exec(ogs *h, void *const *u, int mode, unsigned vn, int dom, int op, in
     /* pw_exec (gs.upc:470-500): pack, deliver, unpack */
     const int recv = 0 ^ t, send = 1 ^ t;
     char **sendbuf = zalloc((size_t)np * sizeof *sendbuf);
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < np; ++p) {
       struct rank_data *r = &h->r[p];
       sendbuf[p] = zalloc((size_t)r->comm[send].total * nv * esz);
       for (unsigned k = 0; k < nv; ++k)      /* buffer layout [slot][vn] (gs_local.c:308-318) */
         scatter_any(sendbuf[p] + (size_t)k * esz, nv, v[p].base[k], v[p].stride, r->pw_map[send], dom);
     }
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < np; ++p) {
       struct rank_data *r = &h->r[p];
       reserve(r, (size_t)r->comm[recv].total * nv * esz + 1);
@@ -530,12 +536,13 @@ void ogs_exec(ogs *h, void *const *u, int mode, unsigned vn, int dom, int op, in
         acc += len;
       }
     }
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < np; ++p) {
       struct rank_data *r = &h->r[p];
       for (unsigned k = 0; k < nv; ++k)
         gather_any(v[p].base[k], v[p].stride, r->buf + (size_t)k * esz, nv, r->pw_map[recv], dom, op);
-      free(sendbuf[p]);
     }
+    for (int p = 0; p < np; ++p) free(sendbuf[p]);
     free(sendbuf);
   } else if (np > 1) {
     /* allreduce_exec (gs.upc:1006-1026); combine in rank order */
@@ -565,6 +572,7 @@ void ogs_exec(ogs *h, void *const *u, int mode, unsigned vn, int dom, int op, in
   }
 
   /* local scatter (gs.upc:1184) */
+#pragma omp parallel for schedule(static)
   for (int p = 0; p < np; ++p) {
     struct rank_data *r = &h->r[p];
     for (unsigned k = 0; k < nv; ++k)
