@@ -84,25 +84,31 @@ struct xg_hmap {
 void xg_hmap_free(struct xg_hmap *m);
 
 /* Sliced-ELL view of a symmetric CSR map (after SELL-C-sigma, Kreutzer et
-   al. 2014, C = 32).  Groups are stably sorted by size class inside windows of
-   `sigma` consecutive groups (so neighbours in the field stay neighbours), and
-   packed into fixed-size blocks of 32 lanes x 8 member slots = 256 indices
-   (1 KB): a block of class W holds 8/W sub-chunks of 32 groups, lane l of
-   sub-chunk s owning slots [s*W, s*W+W) of its 8.  Each lane's 8 slots are
-   contiguous, so a warp reads a block with two coalesced 128-bit loads per
-   lane and then has 8 independent field loads in flight per lane whatever the
-   group size.  No per-group offsets remain; one class byte per block.
-   Unused slots hold XG_NONE.  Groups with more than 8 members stay in a
-   residual CSR.                                                             */
+   al. 2014, C = 32), shaped for one warp per block and one CTA per window:
+
+   block   32 lanes x 8 member slots = 256 indices (1 KB).  A lane's 8 slots
+           are contiguous (two 128-bit loads) and hold whole groups back to
+           back; bit j of the lane's start mask says "slot j begins a group".
+           Unused slots hold XG_NONE.  Whatever the group sizes, every lane
+           has 8 independent field loads in flight.
+   window  XG_SELL_WB consecutive blocks = the consecutive groups (in primary
+           order) that fill them, stably sorted by descending size and dealt
+           row-major over the lanes, so lanes next to each other hold groups
+           next to each other in the field and groups of all sizes that touch
+           the same stretch of the field meet in the same CTA's L1.
+
+   No per-group offsets remain: 4 bytes per member + 1 mask byte per lane.
+   Groups with more than 8 members stay in a residual CSR.                   */
 #define XG_SELL_WMAX 8
+#define XG_SELL_WB   8     /* blocks per window = warps per CTA */
 struct xg_sell {
-  u32  nblock;        /* blocks of 256 indices                               */
-  unsigned char *cls; /* [nblock] 2, 4 or 8                                  */
+  u32  nblock;        /* multiple of XG_SELL_WB                              */
+  unsigned char *mask;/* [nblock*32] start mask of each lane                 */
   u32 *idx;           /* [nblock*256]                                        */
   size_t nidx;
   struct xg_hmap rest;/* groups with more than XG_SELL_WMAX members          */
 };
-void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m, u32 sigma);
+void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m);
 void xg_sell_free(struct xg_sell *s);
 void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m);
 u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *count);
@@ -168,7 +174,7 @@ struct xcu_csr {
 /* device SELL map */
 struct xcu_sell {
   u32 nblock;
-  const unsigned char *cls;
+  const unsigned char *mask;
   const u32 *idx;
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,

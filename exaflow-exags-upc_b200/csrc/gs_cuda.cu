@@ -175,46 +175,42 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 
 // ---------------------------------------------------------------------------
 // k_fused_sell: the hot kernel.  One warp per 1 KB block of the sliced-ELL
-// map (struct xg_sell): lane l owns 8 consecutive member slots, fetched with
-// two coalesced 128-bit loads; there is no offset array and no dependent
-// offset->index load.  A block of class W packs 8/W groups per lane, so every
-// lane keeps 8 independent field loads in flight whether the mesh's groups
-// have 2, 4 or 8 members (faces, edges, corners of hex elements).  Each group
-// is still reduced left to right by one thread -- the reference's association
-// order (src/gs_local.c:60-71) -- and the result is written to every member
-// (src/gs_local.c:76-87), gather and scatter fused in one pass.
+// map (struct xg_sell), one CTA per window of 8 blocks.  Lane l owns 8
+// consecutive member slots, fetched with two coalesced 128-bit loads, plus one
+// start-mask byte; there is no offset array and no dependent offset->index
+// load, and every lane keeps 8 independent field loads in flight whether the
+// mesh's groups have 2, 4 or 8 members (faces, edges, corners of hex
+// elements).  The 8 slots are then reduced as a segmented left-to-right scan
+// (forward pass) and the segment totals are copied back over the segment
+// (backward pass): each group is summed by one thread in the reference's
+// association order (src/gs_local.c:60-71) and its result is written to every
+// member (src/gs_local.c:76-87) -- gather and scatter fused in one pass over
+// the field.  Both passes are select-based, so lanes with different group
+// layouts do not diverge.
 // ---------------------------------------------------------------------------
-template <typename T, int OP, int W>
-__device__ __forceinline__ void sell_reduce_store(const u32 (&id)[8], T (&x)[8])
-{
-#pragma unroll
-  for (int s = 0; s < 8; s += W) {
-    T v = x[s];
-#pragma unroll
-    for (int q = 1; q < W; ++q) if (id[s + q] != XG_NONE) v = apply<T, OP>(v, x[s + q]);
-#pragma unroll
-    for (int q = 0; q < W; ++q) x[s + q] = v;
-  }
-}
-
 template <typename T, int OP, int MODE, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
 k_fused_sell(xcu_sell m, Fld<T, MODE> f)
 {
-  const u32 c = blockIdx.x * 8u + (threadIdx.x >> 5);
-  if (c >= m.nblock) return;
+  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
   const uint4 a = __ldg(p), b = __ldg(p + 1);
-  const unsigned w = __ldg(m.cls + c);
+  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   for (unsigned k = 0; k < f.vn; ++k) {
     T x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) x[j] = *f.at(id[j], k);
-    if (w == 2u)      sell_reduce_store<T, OP, 2>(id, x);
-    else if (w == 4u) sell_reduce_store<T, OP, 4>(id, x);
-    else              sell_reduce_store<T, OP, 8>(id, x);
+    // forward: running reduction, restarted where a group begins
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[j - 1], x[j]) : x[j - 1];
+      x[j] = ((start >> j) & 1u) ? x[j] : cont;
+    }
+    // backward: the last slot of a group holds its total; spread it
+#pragma unroll
+    for (int j = 6; j >= 0; --j) x[j] = ((start >> (j + 1)) & 1u) ? x[j] : x[j + 1];
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) *f.at(id[j], k) = x[j];
   }
@@ -400,22 +396,23 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
 {
   if (!m->nblock) return;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (m->nblock + 7u) / 8u;
+  const unsigned grid = m->nblock / XG_SELL_WB;
+  const unsigned nthr = 32 * XG_SELL_WB;
   static int variant = -1;
   if (variant < 0) { const char *v = getenv("EXAGS_SELL_VARIANT"); variant = v ? atoi(v) : 0; }
   if (variant == 0) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, MODE, 5><<<grid, 256, 0, st>>>(*m, make_fld<T, MODE>(f))
+  k_fused_sell<T, OP, MODE, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, MODE>(f))
   FOR_ALL(X)
 #undef X
   } else if (mode == XM_PLAIN && xdom == XD_F64 && xop == XO_ADD) {
     /* tuning variants (occupancy targets), gs(add,double) only */
     Fld<double, XM_PLAIN> fl = make_fld<double, XM_PLAIN>(f);
     switch (variant) {
-      case 1: k_fused_sell<double, XO_ADD, XM_PLAIN, 4><<<grid, 256, 0, st>>>(*m, fl); break;
-      case 2: k_fused_sell<double, XO_ADD, XM_PLAIN, 6><<<grid, 256, 0, st>>>(*m, fl); break;
-      case 3: k_fused_sell<double, XO_ADD, XM_PLAIN, 7><<<grid, 256, 0, st>>>(*m, fl); break;
-      default: k_fused_sell<double, XO_ADD, XM_PLAIN, 8><<<grid, 256, 0, st>>>(*m, fl); break;
+      case 1: k_fused_sell<double, XO_ADD, XM_PLAIN, 4><<<grid, nthr, 0, st>>>(*m, fl); break;
+      case 2: k_fused_sell<double, XO_ADD, XM_PLAIN, 5><<<grid, nthr, 0, st>>>(*m, fl); break;
+      case 3: k_fused_sell<double, XO_ADD, XM_PLAIN, 7><<<grid, nthr, 0, st>>>(*m, fl); break;
+      default: k_fused_sell<double, XO_ADD, XM_PLAIN, 8><<<grid, nthr, 0, st>>>(*m, fl); break;
     }
   } else exags_fail(1, __FILE__, __LINE__, "EXAGS_SELL_VARIANT is a tuning knob for gs(add,double) only");
   LAUNCHED();

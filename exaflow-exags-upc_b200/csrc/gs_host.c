@@ -305,16 +305,15 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   const char *lay = getenv("EXAGS_LAYOUT");
   int use_sell = !in.nunf && in.ng && !(lay && strcmp(lay, "csr") == 0);
   if (use_sell) {
-    const char *tg = getenv("EXAGS_SELL_SIGMA");
-    xg_sell_build(&sell, &in, tg && atoi(tg) > 0 ? (u32)atoi(tg) : 8192u);
+    xg_sell_build(&sell, &in);
     g->sell_idx_entries = sell.nidx;
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
     g->d_sell.nblock = sell.nblock;
-    g->d_sell_mem[0] = upload(sell.cls, (size_t)(sell.nblock ? sell.nblock : 1));
+    g->d_sell_mem[0] = upload(sell.mask, (size_t)sell.nblock * 32 + 1);
     g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
-    g->d_sell.cls = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
+    g->d_sell.mask = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
   }
   if (g->on_device) {
     if (!use_sell) upload_csr(&g->d_int, &in);

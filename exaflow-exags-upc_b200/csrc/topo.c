@@ -174,18 +174,17 @@ u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *c
 /* ------------------------------------------------------------------ */
 void xg_sell_free(struct xg_sell *s)
 {
-  free(s->cls); free(s->idx);
+  free(s->mask); free(s->idx);
   xg_hmap_free(&s->rest);
   memset(s, 0, sizeof *s);
 }
 
-static inline int sell_class(u32 size) { return size <= 2 ? 0 : size <= 4 ? 1 : 2; }
+static inline u32 sell_width(u32 size) { return size <= 2 ? 2u : size <= 4 ? 4u : 8u; }
 
-void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m, u32 sigma)
+void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
 {
-  static const u32 W[3] = { 2, 4, 8 }, GPB[3] = { 128, 64, 32 };   /* groups per block */
+  const u32 WSLOTS = XG_SELL_WB * 256u;            /* member slots per window */
   memset(s, 0, sizeof *s);
-  if (sigma < 128) sigma = 128;
   /* long groups go to the residual CSR */
   size_t nlong = 0, ilong = 0, nshort = 0;
   for (u32 g = 0; g < m->ng; ++g) {
@@ -208,48 +207,75 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m, u32 sigma)
     }
     s->rest.off[nlong] = (u32)oi;
   }
-  size_t nwin = (nshort + sigma - 1) / sigma;
-  /* pass 1: blocks per window */
-  u32 *wstart = xnew(u32, nwin + 1);
-  size_t nblock = 0;
-  for (size_t w = 0; w < nwin; ++w) {
-    size_t g0 = w * sigma, g1 = g0 + sigma < nshort ? g0 + sigma : nshort;
-    u32 cnt[3] = { 0, 0, 0 };
-    for (size_t k = g0; k < g1; ++k) ++cnt[sell_class(m->off[sg[k] + 1] - m->off[sg[k]])];
-    wstart[w] = (u32)nblock;
-    for (int c = 0; c < 3; ++c) nblock += (cnt[c] + GPB[c] - 1) / GPB[c];
+  /* windows: greedy runs of consecutive groups whose padded widths fill
+     WSLOTS; power-of-two widths dealt in descending order always pack, so a
+     window is full exactly when its widths add up to WSLOTS */
+  size_t nwin = 0;
+  for (size_t k = 0; k < nshort;) {
+    u32 used = 0;
+    while (k < nshort) {
+      u32 w = sell_width(m->off[sg[k] + 1] - m->off[sg[k]]);
+      if (used + w > WSLOTS) break;
+      used += w; ++k;
+    }
+    ++nwin;
   }
-  wstart[nwin] = (u32)nblock;
-  if (nblock >> 23) xfail("gs_setup: map too large for the sliced layout");
-  s->nblock = (u32)nblock;
-  s->nidx = nblock * 256;
-  s->cls = xnew(unsigned char, nblock ? nblock : 1);
+  size_t *wfirst = xnew(size_t, nwin + 1);
+  {
+    size_t w = 0;
+    for (size_t k = 0; k < nshort;) {
+      u32 used = 0;
+      wfirst[w++] = k;
+      while (k < nshort) {
+        u32 wd = sell_width(m->off[sg[k] + 1] - m->off[sg[k]]);
+        if (used + wd > WSLOTS) break;
+        used += wd; ++k;
+      }
+    }
+    wfirst[nwin] = nshort;
+  }
+  if ((nwin * XG_SELL_WB) >> 23) xfail("gs_setup: map too large for the sliced layout");
+  s->nblock = (u32)(nwin * XG_SELL_WB);
+  s->nidx = (size_t)s->nblock * 256;
+  s->mask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
-  /* pass 2: fill, windows are independent */
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 16)
+#pragma omp parallel
 #endif
-  for (size_t w = 0; w < nwin; ++w) {
-    size_t g0 = w * sigma, g1 = g0 + sigma < nshort ? g0 + sigma : nshort;
-    size_t blk = wstart[w];
-    for (int c = 0; c < 3; ++c) {
-      size_t in_class = 0;
-      u32 *base = 0;
-      for (size_t k = g0; k < g1; ++k) {
-        u32 g = sg[k], a = m->off[g], sz = m->off[g + 1] - a;
-        if (sell_class(sz) != c) continue;
-        size_t j = in_class % GPB[c];
-        if (j == 0) {                       /* open a new block */
-          base = s->idx + blk * 256;
-          for (int z = 0; z < 256; ++z) base[z] = XG_NONE;
-          s->cls[blk] = (unsigned char)W[c];
-          ++blk;
+  {
+    unsigned char fill[XG_SELL_WB * 32];
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+    for (size_t w = 0; w < nwin; ++w) {
+      u32 *base = s->idx + w * WSLOTS;
+      unsigned char *mk = s->mask + w * XG_SELL_WB * 32;
+      for (u32 z = 0; z < WSLOTS; ++z) base[z] = XG_NONE;
+      memset(fill, 0, sizeof fill);
+      /* descending width, stable in primary order; rows of equal width are
+         dealt lane after lane, block after block */
+      for (u32 wd = 8; wd >= 2; wd >>= 1) {
+        u32 pos = 0;                                /* lane cursor over the window */
+        for (size_t k = wfirst[w]; k < wfirst[w + 1]; ++k) {
+          u32 g = sg[k], a = m->off[g], sz = m->off[g + 1] - a;
+          if (sell_width(sz) != wd) continue;
+          /* next lane (block-major, then lane) with room; fills are multiples
+             of wd here, and lanes before the cursor are at least as full */
+          u32 tries = 0;
+          while (fill[pos] + wd > 8) {
+            pos = (pos + 1) % (XG_SELL_WB * 32);
+            if (++tries > XG_SELL_WB * 32) xfail("gs_setup: internal error packing the sliced layout");
+          }
+          u32 *slot = base + (size_t)pos * 8 + fill[pos];
+          for (u32 q = 0; q < sz; ++q) slot[q] = m->idx[a + q];
+          mk[pos] |= (unsigned char)(1u << fill[pos]);
+          fill[pos] = (unsigned char)(fill[pos] + wd);
+          /* row-major dealing: move on to the next lane; wrap to start a new
+             row of this width */
+          pos = (pos + 1) % (XG_SELL_WB * 32);
         }
-        u32 lane = (u32)(j & 31u), sub = (u32)(j >> 5);
-        for (u32 q = 0; q < sz; ++q) base[lane * 8 + sub * W[c] + q] = m->idx[a + q];
-        ++in_class;
       }
     }
   }
-  free(wstart); free(sg);
+  free(wfirst); free(sg);
 }
