@@ -288,3 +288,36 @@ def test_kernels_really_launch(X):
     X.gs(_dev(np.ones(ids.size)), X.gs_double, X.gs_add, 0, g)
     assert X.kernel_launches() > before
     X.gs_free(g)
+
+
+import glob as _glob
+import os as _os
+
+_GOLD1 = sorted(p for p in _glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "*.npz"))
+                if "_np1" in p or "config1" in p)
+
+
+@pytest.mark.parametrize("path", _GOLD1, ids=[_os.path.basename(p) for p in _GOLD1])
+def test_golden_from_reference_on_gpu(X, path):
+    """The CUDA path against fixtures produced by the reference's own compiled
+    sources (oracle/make_golden.py): bit-exact, every case."""
+    z = np.load(path)
+    ids = z["id0"]
+    g = X.gs_setup(ids, unique=int(z["unique"]))
+    for w in (0, 1, 2):
+        assert np.array_equal(g.dump_map(w), z[f"map{w}_0"])
+    k = 0
+    while f"case{k}_meta" in z:
+        mode, vn, dom, op, t = [int(x) for x in z[f"case{k}_meta"]]
+        a = z[f"case{k}_in0"].copy()
+        if mode == 2:
+            d = [_dev(a[i]) for i in range(vn)]
+            X.gs_many(d, vn, dom, op, t, g)
+            got = np.stack([x.cpu().numpy() for x in d])
+        else:
+            d = _dev(a)
+            (X.gs(d, dom, op, t, g) if mode == 0 else X.gs_vec(d, vn, dom, op, t, g))
+            got = d.cpu().numpy()
+        assert np.array_equal(got, z[f"case{k}_out0"]), (path, k)
+        k += 1
+    X.gs_free(g)
