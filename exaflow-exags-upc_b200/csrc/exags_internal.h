@@ -50,6 +50,7 @@ void *xrealloc_(void *p, size_t bytes, const char *file, unsigned line);
 #define xgrow(T, p, n)    ((T *)xrealloc_((p), (size_t)(n) * sizeof(T), __FILE__, __LINE__))
 
 /* ---- sorting (sort.c) --------------------------------------------------- */
+int xg_setup_threads(void);
 /* Stable LSD radix sort of (key,val) pairs on the low `bits` bits of key.
    tmpk/tmpv are scratch of n entries; result ends up back in key/val.      */
 void xsort_u64_u32(u64 *key, u32 *val, size_t n, unsigned bits,

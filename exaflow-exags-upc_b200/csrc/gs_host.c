@@ -416,6 +416,9 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
 
   xg_plan_build(&g->plan, &sh, &topo);
   split_groups(g, &topo);
+  /* the NCCL communicator is created here, collectively, never lazily inside
+     a ncclGroupStart/End bracket */
+  if (np > 1 && g->on_device) (void)xg_world_nccl(w);
   xg_shared_free(&sh);
   xg_topo_free(&topo);
   free(id_own);

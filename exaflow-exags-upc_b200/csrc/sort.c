@@ -18,10 +18,36 @@
 #define DIGIT_BITS 11
 #define NBINS (1u << DIGIT_BITS)
 
+/* Threads for the setup phase.  gs_setup is a collective bulk phase, so each
+   rank takes its share of the node's cores regardless of OMP_NUM_THREADS
+   (launchers such as torchrun force that to 1); EXAGS_SETUP_THREADS overrides. */
+int xg_setup_threads(void)
+{
+#ifdef _OPENMP
+  static int cached = 0;
+  if (!cached) {
+    const char *e = getenv("EXAGS_SETUP_THREADS");
+    int t = e ? atoi(e) : 0;
+    if (t <= 0) {
+      const char *lw = getenv("LOCAL_WORLD_SIZE"), *ws = getenv("WORLD_SIZE");
+      int ranks = lw ? atoi(lw) : ws ? atoi(ws) : 1;
+      if (ranks < 1) ranks = 1;
+      t = omp_get_num_procs() / ranks;
+    }
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    cached = t;
+  }
+  return cached;
+#else
+  return 1;
+#endif
+}
+
 static int sort_threads(size_t n)
 {
 #ifdef _OPENMP
-  int t = omp_get_max_threads();
+  int t = xg_setup_threads();
   size_t cap = n / 65536 + 1;
   if ((size_t)t > cap) t = (int)cap;
   if (t > 64) t = 64;

@@ -103,7 +103,7 @@ void xg_topo_build(struct xg_topo *t, const i64 *id, size_t n)
     t->gstart[ngrp] = run;
   }
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(xg_setup_threads())
 #endif
   for (size_t g = 0; g < ngrp; ++g) {
     u32 s = order[g], a = gs0[s], b = gs0[s + 1], o = t->gstart[g];
@@ -240,7 +240,7 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   s->mask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
 #ifdef _OPENMP
-#pragma omp parallel
+#pragma omp parallel num_threads(xg_setup_threads())
 #endif
   {
     unsigned char fill[XG_SELL_WB * 32];
