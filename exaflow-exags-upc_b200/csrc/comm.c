@@ -60,11 +60,15 @@ struct xg_world {
   /* device side */
   void *stream[2];
   void *event[4];
-  void *scratch[3];
-  size_t scratch_bytes[3];
+  void *scratch[4];
+  size_t scratch_bytes[4];
   /* nccl */
   void *nccl_lib;
   void *nccl_comm;
+  /* cuda-ipc transport */
+  int use_ipc;
+  void *ipc_mine; size_t ipc_bytes;
+  void **ipc_peer;
 };
 
 static struct xg_world *g_world = 0;
@@ -412,6 +416,20 @@ struct xg_world *xg_world_get(void)
     for (int i = 0; i < 4; ++i) w->event[i] = xcu_event_create();
   }
   if (w->np > 1) rendezvous_attach(w);
+  if (w->np > 1 && w->has_cuda) {
+    /* NCCL cannot place two ranks on one device: fall back to CUDA-IPC pulls */
+    char mine[16], *all = xnew(char, 16 * (size_t)w->np);
+    xcu_device_uuid(w->device, mine);
+    xg_host_allgather(w, mine, 16, all);
+    for (int p = 0; p < w->np; ++p)
+      for (int q = p + 1; q < w->np; ++q)
+        if (memcmp(all + 16 * p, all + 16 * q, 16) == 0) w->use_ipc = 1;
+    free(all);
+    const char *ex = getenv("EXAGS_EXCHANGE");
+    if (ex && strcmp(ex, "ipc") == 0) w->use_ipc = 1;
+    if (ex && strcmp(ex, "nccl") == 0) w->use_ipc = 0;
+    w->ipc_peer = xnew0(void *, w->np);
+  }
   g_world = w;
   atexit(world_atexit);
   return w;
@@ -433,6 +451,32 @@ void *xg_world_scratch(struct xg_world *w, int which, size_t bytes)
   }
   return w->scratch[which];
 }
+
+int xg_world_ipc(const struct xg_world *w) { return w->use_ipc; }
+
+void *xg_ipc_buffer(struct xg_world *w, size_t bytes)
+{
+  if (w->ipc_bytes >= bytes && w->ipc_mine) return w->ipc_mine;
+  /* `bytes` is identical on every rank, so every rank grows in the same call */
+  xcu_device_sync();
+  xg_host_barrier(w);
+  for (int p = 0; p < w->np; ++p) if (w->ipc_peer[p]) { xcu_ipc_close(w->ipc_peer[p]); w->ipc_peer[p] = 0; }
+  xg_host_barrier(w);
+  if (w->ipc_mine) xcu_free(w->ipc_mine);
+  size_t want = bytes + bytes / 2 + 4096;
+  w->ipc_mine = xcu_malloc(want);
+  w->ipc_bytes = want;
+  char h[64], *all = xnew(char, 64 * (size_t)w->np);
+  xcu_ipc_export(h, w->ipc_mine);
+  xg_host_allgather(w, h, 64, all);
+  for (int p = 0; p < w->np; ++p)
+    if (p != w->rank) w->ipc_peer[p] = xcu_ipc_open(all + 64 * p);
+  free(all);
+  xg_host_barrier(w);
+  return w->ipc_mine;
+}
+
+void *xg_ipc_peer(struct xg_world *w, int rank) { return rank == w->rank ? w->ipc_mine : w->ipc_peer[rank]; }
 
 void exags_set_device(int device) { g_device_override = device; }
 int exags_get_device(void) { return g_world ? g_world->device : g_device_override; }

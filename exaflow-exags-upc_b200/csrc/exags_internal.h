@@ -127,6 +127,14 @@ void *xg_world_nccl(struct xg_world *w);       /* ncclComm_t, created lazily */
    reference's file-static buffer, src/gs.upc:35): 0 send, 1 recv, 2 stage   */
 void *xg_world_scratch(struct xg_world *w, int which, size_t bytes);
 
+/* exchange transport between ranks' GPUs: 0 = NCCL send/recv (default),
+   1 = CUDA-IPC pulls (chosen when two ranks share a device, or EXAGS_EXCHANGE=ipc) */
+int   xg_world_ipc(const struct xg_world *w);
+/* collective: every rank's exported buffer holds at least `bytes` (same value
+   on all ranks); returns this rank's buffer */
+void *xg_ipc_buffer(struct xg_world *w, size_t bytes);
+void *xg_ipc_peer(struct xg_world *w, int rank);   /* mapped pointer to rank's buffer */
+
 /* host-side collectives over the rendezvous segment (np>1) */
 void  xg_host_barrier(struct xg_world *w);
 /* every rank contributes `bytes` bytes; out receives np*bytes, rank-major   */
@@ -157,6 +165,10 @@ void   xcu_device_sync(void);
 void  *xcu_host_alloc(size_t bytes);
 void   xcu_host_free(void *p);
 unsigned long long xcu_launch_count(void);
+void   xcu_ipc_export(void *handle64, void *devptr);
+void  *xcu_ipc_open(const void *handle64);
+void   xcu_ipc_close(void *p);
+void   xcu_device_uuid(int dev, char out16[16]);
 
 /* a field as the kernels see it */
 struct xcu_field {

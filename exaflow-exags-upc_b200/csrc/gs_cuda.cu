@@ -20,6 +20,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "exags_internal.h"
 
 // ---------------------------------------------------------------------------
@@ -573,6 +574,30 @@ void *xcu_event_create(void)
 void xcu_event_record(void *ev, void *st) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
 void xcu_stream_wait_event(void *st, void *ev) { CU(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0)); }
 void xcu_device_sync(void) { CU(cudaDeviceSynchronize()); }
+/* CUDA IPC, for ranks that share a GPU (NCCL refuses two ranks on one device) */
+void xcu_ipc_export(void *handle64, void *devptr)
+{
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, devptr));
+  static_assert(sizeof(h) == 64, "ipc handle size");
+  memcpy(handle64, &h, 64);
+}
+void *xcu_ipc_open(const void *handle64)
+{
+  cudaIpcMemHandle_t h;
+  void *p = 0;
+  memcpy(&h, handle64, 64);
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return p;
+}
+void xcu_ipc_close(void *p) { if (p) CU(cudaIpcCloseMemHandle(p)); }
+void xcu_device_uuid(int dev, char out16[16])
+{
+  cudaDeviceProp pr;
+  CU(cudaGetDeviceProperties(&pr, dev));
+  memcpy(out16, &pr.uuid, 16);
+}
+
 void *xcu_host_alloc(size_t bytes)
 {
   void *p = 0;

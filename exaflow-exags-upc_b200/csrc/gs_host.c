@@ -101,6 +101,46 @@ static void exchange_pairwise(struct gs_data *g, unsigned vn, int xd, int transp
   xg_nccl_group_end(g->w);
 }
 
+/* Pull transport (ranks sharing a GPU, or EXAGS_EXCHANGE=ipc): senders pack
+   into an IPC-exported buffer, a host barrier says "packed", receivers copy
+   their segments out of the peers' buffers with the copy engine, a second
+   barrier says "pulled".  No kernel ever waits on another rank.  It costs two
+   host round trips per call, so NCCL is the default wherever it can run.    */
+static void exchange_ipc_pairwise(struct gs_data *g, unsigned vn, int xd, int transpose,
+                                  void *recvbuf, void *stream)
+{
+  const struct xg_plan *pl = &g->plan;
+  const int rd = 0 ^ transpose;
+  const size_t unit = (size_t)vn * xg_dom_bytes(xd);
+  xcu_stream_sync(stream);
+  xg_host_barrier(g->w);
+  for (u32 k = 0; k < pl->nnb[rd]; ++k)
+    xcu_d2d((char *)recvbuf + (size_t)pl->nb_start[rd][k] * unit,
+            (const char *)xg_ipc_peer(g->w, (int)pl->nb_rank[rd][k]) + (size_t)pl->nb_peer_start[rd][k] * unit,
+            (size_t)pl->nb_size[rd][k] * unit, stream);
+  xcu_stream_sync(stream);
+  xg_host_barrier(g->w);
+}
+
+/* all-reduce on the pull transport: every rank folds all ranks' dense
+   vectors in rank order (identical result everywhere) */
+static void exchange_ipc_allreduce(struct gs_data *g, void *acc, size_t count, int xd, int xop, void *stream)
+{
+  struct xg_world *w = g->w;
+  const int np = xg_world_np(w);
+  const size_t bytes = count * xg_dom_bytes(xd);
+  void *tmp = xg_world_scratch(w, 1, bytes ? bytes : 1);
+  xcu_stream_sync(stream);
+  xg_host_barrier(w);
+  xcu_d2d(acc, xg_ipc_peer(w, 0), bytes, stream);
+  for (int p = 1; p < np; ++p) {
+    xcu_d2d(tmp, xg_ipc_peer(w, p), bytes, stream);
+    xcu_array_op(stream, acc, tmp, count, xd, xop);
+  }
+  xcu_stream_sync(stream);
+  xg_host_barrier(w);
+}
+
 /* ------------------------------------------------------------------ */
 /*  the operator                                                       */
 /* ------------------------------------------------------------------ */
@@ -125,7 +165,10 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
   if (multi) {
     const struct xg_plan *pl = &g->plan;
     scomm = xg_world_stream(w, 1);
-    if (allred) {
+    if (xg_world_ipc(w)) {
+      sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
+      recvbuf = xg_world_scratch(w, allred ? 3 : 1, (size_t)pl->max_total * vn * esz);
+    } else if (allred) {
       sendbuf = xg_world_scratch(w, 0, (size_t)pl->total_shared * vn * esz);
       recvbuf = sendbuf;
     } else {
@@ -159,7 +202,10 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
   if (multi) {
-    if (allred) xg_nccl_allreduce(w, sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
+    if (xg_world_ipc(w)) {
+      if (allred) exchange_ipc_allreduce(g, recvbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
+      else exchange_ipc_pairwise(g, vn, xd, transpose, recvbuf, scomm);
+    } else if (allred) xg_nccl_allreduce(w, sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
     else exchange_pairwise(g, vn, xd, transpose, sendbuf, recvbuf, scomm);
     for (unsigned k0 = 0; k0 < vn; k0 += step) {
       struct xcu_field f; memset(&f, 0, sizeof f);
@@ -418,7 +464,8 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
   split_groups(g, &topo);
   /* the NCCL communicator is created here, collectively, never lazily inside
      a ncclGroupStart/End bracket */
-  if (np > 1 && g->on_device) (void)xg_world_nccl(w);
+  if (np > 1) xg_plan_exchange_offsets(&g->plan, w);
+  if (np > 1 && g->on_device && !xg_world_ipc(w)) (void)xg_world_nccl(w);
   xg_shared_free(&sh);
   xg_topo_free(&topo);
   free(id_own);

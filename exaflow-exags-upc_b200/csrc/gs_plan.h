@@ -33,6 +33,11 @@ struct xg_plan {
   u32 *slot[2];       /* [total] slots, ascending remote rank              */
   u32  nnb[2];        /* neighbour ranks                                   */
   u32 *nb_rank[2], *nb_start[2], *nb_size[2];
+  /* for the pull (CUDA-IPC) transport: where my message starts in the
+     neighbour's send numbering of the same direction, and the largest slot
+     count of any rank/direction (uniform buffer sizing) */
+  u32 *nb_peer_start[2];
+  u64  max_total;
 };
 
 void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w);
@@ -41,6 +46,7 @@ void xg_unique_flags(unsigned char *newflag, size_t n, const struct xg_topo *t,
                      struct xg_shared *sh, int me);
 void xg_plan_build(struct xg_plan *pl, struct xg_shared *sh, const struct xg_topo *t);
 void xg_plan_free(struct xg_plan *pl);
+void xg_plan_exchange_offsets(struct xg_plan *pl, struct xg_world *w);
 
 /* NCCL wrappers (comm.c) */
 void xg_nccl_group_start(struct xg_world *w);

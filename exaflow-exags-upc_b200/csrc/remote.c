@@ -205,7 +205,7 @@ void xg_plan_free(struct xg_plan *pl)
   free(pl->bprim); free(pl->bgrp);
   for (int d = 0; d < 2; ++d) {
     free(pl->soff[d]); free(pl->slot[d]);
-    free(pl->nb_rank[d]); free(pl->nb_start[d]); free(pl->nb_size[d]);
+    free(pl->nb_rank[d]); free(pl->nb_start[d]); free(pl->nb_size[d]); free(pl->nb_peer_start[d]);
   }
   free(pl->ord); free(pl->pflag);
   memset(pl, 0, sizeof *pl);
@@ -296,4 +296,44 @@ void xg_plan_build(struct xg_plan *pl, struct xg_shared *sh, const struct xg_top
   }
   free(bof); free(perm);
   (void)nbits64;
+}
+
+/* Tell every neighbour where its message starts in my numbering, so a
+   receiver can pull its segment straight out of the sender's buffer.  A
+   message I receive in direction d was numbered by its sender in direction d
+   too: slots of direction 0 carry "remote unflagged" rows on the receiving
+   side and "local unflagged" rows on the sending side of the same transfer,
+   i.e. my recv table of direction rd pairs with the peer's send table of
+   direction 1^rd (src/gs.upc:479, 578-584).                                  */
+void xg_plan_exchange_offsets(struct xg_plan *pl, struct xg_world *w)
+{
+  const int np = xg_world_np(w), me = xg_world_rank(w);
+  /* row: {from, to, direction, start} */
+  struct row { u32 from, to, d, start; };
+  size_t *cnt = xnew0(size_t, np), *pos = xnew(size_t, np), *rcnt = xnew(size_t, np), nrecv = 0;
+  for (int d = 0; d < 2; ++d) for (u32 k = 0; k < pl->nnb[d]; ++k) ++cnt[pl->nb_rank[d][k]];
+  size_t tot = 0; for (int p = 0; p < np; ++p) { pos[p] = tot; tot += cnt[p]; }
+  struct row *send = xnew(struct row, tot ? tot : 1);
+  for (int d = 0; d < 2; ++d)
+    for (u32 k = 0; k < pl->nnb[d]; ++k) {
+      struct row *r = send + pos[pl->nb_rank[d][k]]++;
+      r->from = (u32)me; r->to = pl->nb_rank[d][k]; r->d = (u32)d; r->start = pl->nb_start[d][k];
+    }
+  struct row *got = (struct row *)xg_host_alltoallv(w, send, sizeof *send, cnt, rcnt, &nrecv);
+  for (int d = 0; d < 2; ++d) {
+    pl->nb_peer_start[d] = xnew0(u32, pl->nnb[d] ? pl->nnb[d] : 1);
+    for (u32 k = 0; k < pl->nnb[d]; ++k) {
+      int found = 0;
+      for (size_t j = 0; j < nrecv; ++j)
+        if (got[j].from == pl->nb_rank[d][k] && got[j].d == (u32)(1 ^ d)) { pl->nb_peer_start[d][k] = got[j].start; found = 1; break; }
+      if (!found) xfail("gs_setup: neighbour %u has no matching message table", pl->nb_rank[d][k]);
+    }
+  }
+  free(send); free(got); free(cnt); free(pos); free(rcnt);
+  u64 mine = pl->total[0] > pl->total[1] ? pl->total[0] : pl->total[1], *all = xnew(u64, np);
+  if (pl->total_shared > mine) mine = pl->total_shared;
+  xg_host_allgather(w, &mine, sizeof mine, all);
+  pl->max_total = 0;
+  for (int p = 0; p < np; ++p) if (all[p] > pl->max_total) pl->max_total = all[p];
+  free(all);
 }

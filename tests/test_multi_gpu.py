@@ -30,3 +30,18 @@ def test_multirank_exec_unique(built, np_, case):
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "exec", 1, 1], timeout=600)
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case,method,unique", [(2, "slab", 1, 0), (3, "random", 1, 0), (4, "blocks", 1, 0),
+                                                    (2, "fixture", 3, 0), (4, "blocks", 3, 0), (2, "slab", 1, 1),
+                                                    (2, "empty", 1, 0)])
+def test_multirank_exec_one_gpu(built, np_, case, method, unique):
+    """np ranks as processes sharing GPU 0: the library detects the shared
+    device and exchanges halos with CUDA-IPC pulls instead of NCCL, so the
+    boundary pack/unpack kernels, the interior/boundary split and the pairwise
+    and all-reduce plans are all exercised on the 1-GPU box, against the oracle."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0"})
+    assert all(c == 0 for c in codes), "\n".join(outs)
