@@ -92,19 +92,44 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 #  CPU arm: the oracle (port of the reference algorithm) on the host cores
 # --------------------------------------------------------------------------
+def _host_cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_arm(steps: int, warmup: int, seconds_budget: float = 25.0) -> dict:
-    """Times the reference CPU algorithm on a bounded sample of the workload:
-    a 64x64xEZs slab stack of the same N=7 mesh, one z-slab per emulated rank
-    (the reference's SPMD threads), ranks run on separate host cores."""
-    import oracle as O
+    """Times the reference CPU path on a bounded sample of the workload: z-slabs
+    of the same 64x64 N=7 mesh, one slab per rank, pairwise exchange, ranks on
+    separate host cores.  Uses the reference's own code (oracle/_ref, built from
+    /root/reference/src by oracle/build_ref.sh; ranks are forked UPC threads and
+    timing follows src/gs.upc:1094-1111: barrier, 2 warm-ups, N timed calls,
+    mean, max over ranks) when that library is present, else the oracle port
+    with ranks on OpenMP threads."""
     from exags_b200 import semmesh
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    ranks = max(1, min(cores, 16))
-    ez_per = 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(ranks))
+    cores = _host_cores()
+    ranks = 1
+    while ranks * 2 <= min(cores, 32):      # the reference runs gs on powers of two
+        ranks *= 2
+    ez_per = 2
     ids = [semmesh.box_ids(EX, EY, ez_per, ORDER, ez0=r * ez_per, Ez_global=ez_per * ranks)
            for r in range(ranks)]
     n_total = sum(a.size for a in ids)
+    sample = (f"{EX}x{EY}x{ez_per * ranks} el N={ORDER} ({n_total} DOF) as {ranks} z-slab ranks, pairwise")
+    try:
+        import ref
+        if not ref.available():
+            raise RuntimeError("oracle/_ref not built")
+        reps = max(3, min(steps, 10))
+        data = [[semmesh.field_values(semmesh.slab_dof_numbers(EX, EY, ez_per, ORDER, r * ez_per), np.float64)
+                 for r in range(ranks)]]
+        _, times = ref.run(ids, [(0, 1, 0, 0, 0)], data, method=1, reps=reps, arena_bytes=(6 << 30))
+        ms = 1e3 * float(times[0])
+        return {"value": n_total / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": ranks, "kind": "reference",
+                "sample": sample + f", reference's own code as forked UPC threads, 2 warm + {reps} timed calls",
+                "ms_per_step": ms, "steps": reps}
+    except Exception as exc:                    # fall back to the port
+        note = f" (oracle/_ref unavailable: {exc})"
+    import oracle as O
+    os.environ["OMP_NUM_THREADS"] = str(ranks)
     orc = O.Oracle(ids, method=O.METHOD_PAIRWISE)
     us = [semmesh.field_values(semmesh.slab_dof_numbers(EX, EY, ez_per, ORDER, r * ez_per), np.float64)
           for r in range(ranks)]
@@ -120,8 +145,8 @@ def cpu_arm(steps: int, warmup: int, seconds_budget: float = 25.0) -> dict:
             break
     ms = 1e3 * t_all / done
     return {"value": n_total / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": ranks, "kind": "port",
-            "sample": f"{EX}x{EY}x{ez_per * ranks} el N={ORDER} ({n_total} DOF) as {ranks} z-slab ranks, "
-                      f"pairwise, {done} steps", "ms_per_step": ms, "steps": done}
+            "sample": sample + f", oracle port on OpenMP threads, {done} steps" + note,
+            "ms_per_step": ms, "steps": done}
 
 
 def run_reference(args) -> None:
@@ -246,15 +271,21 @@ def run_gpu(args) -> None:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes": b_alg, "kernel": "k_fused<double,add,plain>",
+                "algorithmic_bytes": b_alg, "kernel": "k_fused_sell<double,add,plain>",
                 "kernel_ms_mean": kern_ms, "kernel_ms_min": per[0], "kernel_ms_median": per[len(per) // 2],
                 "frac_vs_8TBps": achieved / 8000.0}
 
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu:
-            cb = cpu_arm(10, 2, seconds_budget=20.0)
-            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # a fresh process: the reference's UPC threads are fork()ed, which
+            # must not happen inside a process that holds a CUDA context
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                                    "--steps", "10", "--warmup", "2"], capture_output=True, text=True, timeout=600)
+                cb = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as exc:
+                cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"cpu baseline failed: {exc}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -58,7 +58,7 @@ struct xg_world {
   unsigned sense;
   unsigned long long epoch;
   /* device side */
-  void *stream[2];
+  void *stream[4];
   void *event[4];
   void *scratch[4];
   size_t scratch_bytes[4];
@@ -413,6 +413,8 @@ struct xg_world *xg_world_get(void)
     xcu_set_device(w->device);
     w->stream[0] = xcu_stream_create(0);
     w->stream[1] = xcu_stream_create(1);
+    w->stream[2] = xcu_stream_create(1);   /* host->device copies of the pipelined host path */
+    w->stream[3] = xcu_stream_create(1);   /* device->host copies */
     for (int i = 0; i < 4; ++i) w->event[i] = xcu_event_create();
   }
   if (w->np > 1) rendezvous_attach(w);

@@ -107,6 +107,8 @@ struct xg_sell {
   unsigned char *mask;/* [nblock*32] start mask of each lane                 */
   u32 *idx;           /* [nblock*256]                                        */
   size_t nidx;
+  u32  nwin;          /* windows = nblock / XG_SELL_WB                       */
+  u32 *win_min, *win_max; /* [nwin] smallest / largest member index per window */
   struct xg_hmap rest;/* groups with more than XG_SELL_WMAX members          */
 };
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m);
@@ -120,7 +122,7 @@ struct xg_world *xg_world_get(void);           /* creates on first use */
 int   xg_world_rank(const struct xg_world *w);
 int   xg_world_np(const struct xg_world *w);
 int   xg_world_has_cuda(const struct xg_world *w);
-void *xg_world_stream(struct xg_world *w, int which);   /* 0 main, 1 comm */
+void *xg_world_stream(struct xg_world *w, int which);   /* 0 main, 1 comm, 2 copy-in, 3 copy-out */
 void *xg_world_event(struct xg_world *w, int which);
 void *xg_world_nccl(struct xg_world *w);       /* ncclComm_t, created lazily */
 /* grow-only device scratch areas owned by the world (the analogue of the

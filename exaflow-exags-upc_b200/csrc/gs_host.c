@@ -40,6 +40,12 @@ struct gs_data {
   struct xcu_sell d_sell;     /* interior groups, sliced-ELL form (symmetric maps) */
   void *d_sell_mem[2];
   size_t sell_idx_entries;
+  /* pipelined host-pointer path (np == 1, symmetric map): chunk schedule */
+  u32 nwin, *win_min, *win_max;       /* host copies from the sliced layout */
+  unsigned pipe_chunks;               /* 0: not available */
+  u32 *pipe_run;                      /* [chunks] windows runnable once chunks 0..k are on the device */
+  u32 *pipe_out_wave;                 /* [chunks] wave after which chunk j is final */
+  void **pipe_ev;                     /* [2*chunks] events */
   u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
   struct xcu_bnd d_bnd;       /* boundary primaries */
   void *d_bnd_mem[10];
@@ -220,6 +226,86 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
   }
 }
 
+/* Host-pointer fast path (np == 1, symmetric sliced-ELL map): the field is cut
+   into contiguous chunks; chunk k goes up on the copy-in stream, the windows
+   whose members all lie in chunks 0..k run as wave k, and chunk j comes back
+   on the copy-out stream as soon as every window that touches it has run.
+   Windows ascend by their first member, so both sets are prefixes of the
+   window list.  PCIe then carries H2D and D2H at the same time and the
+   kernels hide under the copies; any map the schedule cannot cover (flagged
+   labels, long groups, ranks > 1) takes the plain stage-run-copy path.       */
+static void pipe_plan(struct gs_data *g)
+{
+  if (g->pipe_chunks || !g->nwin) return;
+  const size_t n = g->n;
+  unsigned C = (unsigned)(((size_t)n * 8 + (24u << 20) - 1) / (24u << 20));
+  if (C < 2) return;
+  if (C > 128) C = 128;
+  const size_t per = (n + C - 1) / C;
+  g->pipe_run = xnew(u32, C); g->pipe_out_wave = xnew(u32, C);
+  u32 r = 0, pm = 0;
+  for (unsigned k = 0; k < C; ++k) {
+    size_t end = (size_t)(k + 1) * per; if (end > n) end = n;     /* chunk k = [k*per, end) */
+    while (r < g->nwin && (g->win_max[r] > pm ? g->win_max[r] : pm) < end) { if (g->win_max[r] > pm) pm = g->win_max[r]; ++r; }
+    if (k == C - 1) r = g->nwin;
+    g->pipe_run[k] = r;
+  }
+  u32 s0 = 0;
+  for (unsigned j = 0; j < C; ++j) {
+    size_t end = (size_t)(j + 1) * per; if (end > n) end = n;
+    while (s0 < g->nwin && g->win_min[s0] < end) ++s0;            /* windows [0,s0) may touch chunk j */
+    unsigned k = j;
+    while (k < C - 1 && g->pipe_run[k] < s0) ++k;
+    g->pipe_out_wave[j] = k;
+  }
+  g->pipe_ev = xnew(void *, 2 * (size_t)C);
+  for (unsigned k = 0; k < 2 * C; ++k) g->pipe_ev[k] = xcu_event_create();
+  g->pipe_chunks = C;
+}
+
+static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
+                                  int xd, int xop)
+{
+  struct xg_world *w = g->w;
+  const unsigned C = g->pipe_chunks;
+  const size_t n = g->n, esz = xg_dom_bytes(xd), per = (n + C - 1) / C;
+  const unsigned parts = mode == XM_MANY ? vn : 1;
+  const size_t tuple = mode == XM_VEC ? vn : 1;           /* elements per index */
+  const size_t each = n * esz * tuple;
+  char *stage = (char *)xg_world_scratch(w, 2, each * parts);
+  void *s_in = xg_world_stream(w, 2), *s_run = xg_world_stream(w, 0), *s_out = xg_world_stream(w, 3);
+  struct xcu_field f; memset(&f, 0, sizeof f);
+  f.vn = vn; f.tuple = vn; f.k0 = 0;
+  if (mode == XM_MANY) { if (vn > XG_MAXV) xfail("gs: internal: pipelined path with %u arrays", vn); for (unsigned k = 0; k < vn; ++k) f.p[k] = stage + each * k; }
+  else f.p[0] = stage;
+  u32 done = 0;
+  unsigned next_out = 0;
+  for (unsigned k = 0; k < C; ++k) {
+    size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
+    for (unsigned p = 0; p < parts; ++p)
+      xcu_h2d(stage + each * p + lo * esz * tuple, (const char *)ptrs[p] + lo * esz * tuple, (hi - lo) * esz * tuple, s_in);
+    xcu_event_record(g->pipe_ev[k], s_in);
+    xcu_stream_wait_event(s_run, g->pipe_ev[k]);
+    if (g->pipe_run[k] > done) {
+      struct xcu_sell m = g->d_sell;
+      m.idx += (size_t)done * XG_SELL_WB * 256; m.mask += (size_t)done * XG_SELL_WB * 32;
+      m.nblock = (g->pipe_run[k] - done) * XG_SELL_WB;
+      xcu_fused_sell(s_run, &m, &f, mode, xd, xop);
+      done = g->pipe_run[k];
+    }
+    xcu_event_record(g->pipe_ev[C + k], s_run);
+    while (next_out < C && g->pipe_out_wave[next_out] <= k) {
+      size_t olo = (size_t)next_out * per, ohi = olo + per < n ? olo + per : n;
+      xcu_stream_wait_event(s_out, g->pipe_ev[C + g->pipe_out_wave[next_out]]);
+      for (unsigned p = 0; p < parts; ++p)
+        xcu_d2h((char *)ptrs[p] + olo * esz * tuple, stage + each * p + olo * esz * tuple, (ohi - olo) * esz * tuple, s_out);
+      ++next_out;
+    }
+  }
+  xcu_stream_sync(s_out);
+  xcu_stream_sync(s_run);
+}
+
 static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned transpose,
                    struct gs_data *g, void *stream, int blocking, const char *who)
 {
@@ -255,6 +341,15 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
     return;
   }
   /* host data: stage through HBM (still GPU compute) */
+  if (g->nwin && !(mode == XM_MANY && vn > XG_MAXV)) {
+    const char *pp = getenv("EXAGS_HOST_PIPELINE");
+    if (!(pp && atoi(pp) == 0)) pipe_plan(g);
+    if (g->pipe_chunks) {
+      gs_run_host_pipelined(g, ptrs, mode, vn, xd, op);
+      free(ptrs);
+      return;
+    }
+  }
   size_t each = n * esz, total = each * vn;
   char *stage = (char *)xg_world_scratch(w, 2, total);
   void **dptr = xnew(void *, vn);
@@ -353,6 +448,12 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   if (use_sell) {
     xg_sell_build(&sell, &in);
     g->sell_idx_entries = sell.nidx;
+  }
+  if (use_sell && !sell.rest.ng && !nfs && !nb) {
+    /* keep what the pipelined host path needs to schedule windows by chunk */
+    g->nwin = sell.nwin;
+    g->win_min = sell.win_min; g->win_max = sell.win_max;
+    sell.win_min = sell.win_max = 0;
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
@@ -537,7 +638,7 @@ void exags_gs_free(struct gs_data *g)
     for (int m = 0; m < 10; ++m) xcu_free(g->d_bnd_mem[m]);
   }
   xg_hmap_free(&g->hall);
-  free(g->hfp);
+  free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);
   xg_plan_free(&g->plan);
   exags_comm_free(&g->comm);
   free(g);

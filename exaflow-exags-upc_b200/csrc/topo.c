@@ -174,7 +174,7 @@ u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *c
 /* ------------------------------------------------------------------ */
 void xg_sell_free(struct xg_sell *s)
 {
-  free(s->mask); free(s->idx);
+  free(s->mask); free(s->idx); free(s->win_min); free(s->win_max);
   xg_hmap_free(&s->rest);
   memset(s, 0, sizeof *s);
 }
@@ -237,6 +237,9 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   if ((nwin * XG_SELL_WB) >> 23) xfail("gs_setup: map too large for the sliced layout");
   s->nblock = (u32)(nwin * XG_SELL_WB);
   s->nidx = (size_t)s->nblock * 256;
+  s->nwin = (u32)nwin;
+  s->win_min = xnew(u32, nwin ? nwin : 1);
+  s->win_max = xnew(u32, nwin ? nwin : 1);
   s->mask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
 #ifdef _OPENMP
@@ -252,6 +255,15 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
       unsigned char *mk = s->mask + w * XG_SELL_WB * 32;
       for (u32 z = 0; z < WSLOTS; ++z) base[z] = XG_NONE;
       memset(fill, 0, sizeof fill);
+      {
+        u32 lo = XG_NONE, hi = 0;
+        for (size_t k = wfirst[w]; k < wfirst[w + 1]; ++k)
+          for (u32 q = m->off[sg[k]]; q < m->off[sg[k] + 1]; ++q) {
+            if (m->idx[q] < lo) lo = m->idx[q];
+            if (m->idx[q] > hi) hi = m->idx[q];
+          }
+        s->win_min[w] = lo; s->win_max[w] = hi;
+      }
       /* descending width, stable in primary order; rows of equal width are
          dealt lane after lane, block after block */
       for (u32 wd = 8; wd >= 2; wd >>= 1) {

@@ -321,3 +321,28 @@ def test_golden_from_reference_on_gpu(X, path):
         assert np.array_equal(got, z[f"case{k}_out0"]), (path, k)
         k += 1
     X.gs_free(g)
+
+
+def test_pipelined_host_path(X):
+    """Host pointers on a field large enough to take the chunked
+    H2D / wave / D2H pipeline (>= 48 MB of doubles): must equal the
+    device-resident result exactly, for plain, vec and many."""
+    dims = (32, 32, 16, 7)
+    ids = semmesh.box_ids(*dims)
+    n = ids.size
+    g = X.gs_setup(ids)
+    rng = np.random.default_rng(3)
+    u = rng.uniform(0.5, 1.5, n)
+    d = _dev(u); X.gs(d, X.gs_double, X.gs_add, 0, g)
+    h = u.copy(); X.gs(h, X.gs_double, X.gs_add, 0, g)
+    assert np.array_equal(h, d.cpu().numpy())
+    v = rng.uniform(0.5, 1.5, 3 * n).astype(np.float32)
+    d = _dev(v); X.gs_vec(d, 3, X.gs_float, X.gs_add, 1, g)
+    h = v.copy(); X.gs_vec(h, 3, X.gs_float, X.gs_add, 1, g)
+    assert np.array_equal(h, d.cpu().numpy())
+    m = [rng.integers(-1000, 1000, n) for _ in range(3)]
+    dm = [_dev(a) for a in m]; X.gs_many(dm, 3, X.gs_long, X.gs_max, 0, g)
+    hm = [a.copy() for a in m]; X.gs_many(hm, 3, X.gs_long, X.gs_max, 0, g)
+    for a, b in zip(hm, dm):
+        assert np.array_equal(a, b.cpu().numpy())
+    X.gs_free(g)
