@@ -189,7 +189,10 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 // the field.  Both passes are select-based, so lanes with different group
 // layouts do not diverge.
 // ---------------------------------------------------------------------------
-template <typename T, int OP, int MODE, int MINB>
+// KU = components handled per pass: 1 for plain fields; 3 for vec/many so the
+// loads of all three components of a velocity field are in flight together
+// (BASELINE config 3) and the index block is read once for all of them.
+template <typename T, int OP, int MODE, int KU, int MINB>
 __global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
 k_fused_sell(xcu_sell m, Fld<T, MODE> f)
 {
@@ -199,21 +202,32 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f)
   const uint4 a = __ldg(p), b = __ldg(p + 1);
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-  for (unsigned k = 0; k < f.vn; ++k) {
-    T x[8];
+  for (unsigned k0 = 0; k0 < f.vn; k0 += KU) {
+    T x[KU][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) x[j] = *f.at(id[j], k);
-    // forward: running reduction, restarted where a group begins
+    for (int kk = 0; kk < KU; ++kk)
+      if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
-    for (int j = 1; j < 8; ++j) {
-      const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[j - 1], x[j]) : x[j - 1];
-      x[j] = ((start >> j) & 1u) ? x[j] : cont;
+        for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) x[kk][j] = *f.at(id[j], k0 + kk);
+      }
+#pragma unroll
+    for (int kk = 0; kk < KU; ++kk) {
+      // forward: running reduction, restarted where a group begins
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
+        x[kk][j] = ((start >> j) & 1u) ? x[kk][j] : cont;
+      }
+      // backward: the last slot of a group holds its total; spread it
+#pragma unroll
+      for (int j = 6; j >= 0; --j) x[kk][j] = ((start >> (j + 1)) & 1u) ? x[kk][j] : x[kk][j + 1];
     }
-    // backward: the last slot of a group holds its total; spread it
 #pragma unroll
-    for (int j = 6; j >= 0; --j) x[j] = ((start >> (j + 1)) & 1u) ? x[j] : x[j + 1];
+    for (int kk = 0; kk < KU; ++kk)
+      if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) *f.at(id[j], k) = x[j];
+        for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) *f.at(id[j], k0 + kk) = x[kk][j];
+      }
   }
 }
 
@@ -399,23 +413,26 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = m->nblock / XG_SELL_WB;
   const unsigned nthr = 32 * XG_SELL_WB;
-  static int variant = -1;
-  if (variant < 0) { const char *v = getenv("EXAGS_SELL_VARIANT"); variant = v ? atoi(v) : 0; }
-  if (variant == 0) {
+  if (mode == XM_PLAIN || f->vn == 1) {
+    /* one component: a vec/many field with vn == 1 is addressed like a plain one */
+    xcu_field f1 = *f;
+    f1.vn = 1; f1.tuple = 1;
+    mode = XM_PLAIN;
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, MODE, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, MODE>(f))
-  FOR_ALL(X)
+  k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
+    FOR_DOM(XM_PLAIN, X)
 #undef X
-  } else if (mode == XM_PLAIN && xdom == XD_F64 && xop == XO_ADD) {
-    /* tuning variants (occupancy targets), gs(add,double) only */
-    Fld<double, XM_PLAIN> fl = make_fld<double, XM_PLAIN>(f);
-    switch (variant) {
-      case 1: k_fused_sell<double, XO_ADD, XM_PLAIN, 4><<<grid, nthr, 0, st>>>(*m, fl); break;
-      case 2: k_fused_sell<double, XO_ADD, XM_PLAIN, 5><<<grid, nthr, 0, st>>>(*m, fl); break;
-      case 3: k_fused_sell<double, XO_ADD, XM_PLAIN, 7><<<grid, nthr, 0, st>>>(*m, fl); break;
-      default: k_fused_sell<double, XO_ADD, XM_PLAIN, 8><<<grid, nthr, 0, st>>>(*m, fl); break;
-    }
-  } else exags_fail(1, __FILE__, __LINE__, "EXAGS_SELL_VARIANT is a tuning knob for gs(add,double) only");
+  } else if (mode == XM_VEC) {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f))
+    FOR_DOM(XM_VEC, X)
+#undef X
+  } else {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f))
+    FOR_DOM(XM_MANY, X)
+#undef X
+  }
   LAUNCHED();
 }
 
