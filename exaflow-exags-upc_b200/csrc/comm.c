@@ -69,6 +69,9 @@ struct xg_world {
   int use_ipc;
   void *ipc_mine; size_t ipc_bytes;
   void **ipc_peer;
+  /* push transport */
+  int use_push;
+  int *push_status;
 };
 
 static struct xg_world *g_world = 0;
@@ -426,11 +429,28 @@ struct xg_world *xg_world_get(void)
     for (int p = 0; p < w->np; ++p)
       for (int q = p + 1; q < w->np; ++q)
         if (memcmp(all + 16 * p, all + 16 * q, 16) == 0) w->use_ipc = 1;
+    /* push transport: every rank must be able to store into every other
+       rank's device (NVLink / PCIe peer access); all ranks take the same
+       decision */
+    char ok = 1, *oks = xnew(char, w->np);
+    for (int p = 0; p < w->np; ++p)
+      if (p != w->rank && memcmp(all + 16 * p, mine, 16) != 0 && !xcu_peer_ok(w->device, all + 16 * p)) ok = 0;
+    xg_host_allgather(w, &ok, 1, oks);
+    for (int p = 0; p < w->np; ++p) ok &= oks[p];
+    free(oks);
     free(all);
     const char *ex = getenv("EXAGS_EXCHANGE");
-    if (ex && strcmp(ex, "ipc") == 0) w->use_ipc = 1;
-    if (ex && strcmp(ex, "nccl") == 0) w->use_ipc = 0;
+    w->use_push = ok && !w->use_ipc;
+    if (ex && strcmp(ex, "ipc") == 0) { w->use_ipc = 1; w->use_push = 0; }
+    if (ex && strcmp(ex, "nccl") == 0) { w->use_ipc = 0; w->use_push = 0; }
+    if (ex && strcmp(ex, "push") == 0) {
+      /* on a shared device (tests) the kernels of different ranks time-slice;
+         the all-reduce method then still needs the pull transport */
+      if (!ok) xfail("comm: EXAGS_EXCHANGE=push but the devices of this job have no peer access");
+      w->use_push = 1;
+    }
     w->ipc_peer = xnew0(void *, w->np);
+    if (w->use_push) { w->push_status = (int *)xcu_host_alloc_mapped(sizeof(int)); *w->push_status = 0; }
   }
   g_world = w;
   atexit(world_atexit);
@@ -479,6 +499,50 @@ void *xg_ipc_buffer(struct xg_world *w, size_t bytes)
 }
 
 void *xg_ipc_peer(struct xg_world *w, int rank) { return rank == w->rank ? w->ipc_mine : w->ipc_peer[rank]; }
+
+int xg_world_push(const struct xg_world *w) { return w->use_push; }
+int *xg_world_push_status(struct xg_world *w) { return w->push_status; }
+
+static void mbox_close(struct xg_world *w, struct xg_mbox *mb)
+{
+  if (!mb->mine) return;
+  /* nobody may still be storing into a mailbox that goes away */
+  xcu_device_sync();
+  xg_host_barrier(w);
+  for (int p = 0; p < w->np; ++p) if (mb->peer && mb->peer[p]) { xcu_ipc_close(mb->peer[p]); mb->peer[p] = 0; }
+  xg_host_barrier(w);
+  xcu_free(mb->mine);
+  mb->mine = 0; mb->data_bytes = 0;
+}
+
+int xg_mbox_ensure(struct xg_world *w, struct xg_mbox *mb, const u32 *nbr, u32 nnbr, size_t data_bytes)
+{
+  if (mb->mine && mb->data_bytes >= data_bytes) return 0;
+  /* data_bytes is the same on every rank, so every rank is here in the same call */
+  mbox_close(w, mb);
+  if (!mb->peer) mb->peer = xnew0(void *, w->np);
+  size_t want = (data_bytes + data_bytes / 4 + 255) & ~(size_t)255;
+  mb->mine = xcu_malloc(XG_MBOX_HDR + 2 * want);
+  mb->data_bytes = want;
+  xcu_memset(mb->mine, 0, XG_MBOX_HDR, 0);
+  xcu_device_sync();
+  char h[64], *all = xnew(char, 64 * (size_t)w->np);
+  xcu_ipc_export(h, mb->mine);
+  xg_host_allgather(w, h, 64, all);
+  for (u32 k = 0; k < nnbr; ++k)
+    if ((int)nbr[k] != w->rank) mb->peer[nbr[k]] = xcu_ipc_open(all + 64 * nbr[k]);
+  free(all);
+  mb->epoch = 0;
+  xg_host_barrier(w);
+  return 1;
+}
+
+void xg_mbox_free(struct xg_world *w, struct xg_mbox *mb)
+{
+  mbox_close(w, mb);
+  free(mb->peer); mb->peer = 0;
+  if (mb->d_tab) { xcu_free(mb->d_tab); mb->d_tab = 0; }
+}
 
 void exags_set_device(int device) { g_device_override = device; }
 int exags_get_device(void) { return g_world ? g_world->device : g_device_override; }

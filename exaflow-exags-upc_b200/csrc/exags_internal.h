@@ -137,6 +137,30 @@ int   xg_world_ipc(const struct xg_world *w);
 void *xg_ipc_buffer(struct xg_world *w, size_t bytes);
 void *xg_ipc_peer(struct xg_world *w, int rank);   /* mapped pointer to rank's buffer */
 
+/* Push transport (default between distinct NVLink-connected GPUs, or
+   EXAGS_EXCHANGE=push): the boundary pack kernel stores each value straight
+   into the receiving rank's mailbox over NVLink and the last CTA to finish
+   raises a flag there; the receiver's stream waits on its own flags, then
+   unpacks.  No NCCL call and no host round trip on the data path -- the
+   B200 counterpart of pw_exec_sends/pw_exec_recvs (src/gs.upc:409-468),
+   whose upc_memput + polled flag it restates with peer stores.  A mailbox
+   belongs to one gs handle; two data areas alternate by call parity.       */
+#define XG_MBOX_HDR 4096u            /* flags u32[np] at 0, CTA counter at 512 */
+struct xg_mbox {
+  void  *mine;                       /* header + 2 data areas                  */
+  size_t data_bytes;                 /* bytes of one data area                 */
+  void **peer;                       /* [np] mapped mailboxes of my neighbours */
+  u32    epoch;                      /* exchanges done on this mailbox         */
+  void  *d_tab;                      /* device tables built by the handle      */
+};
+int   xg_world_push(const struct xg_world *w);
+int  *xg_world_push_status(struct xg_world *w);   /* pinned+mapped int, 0 = ok */
+/* collective over the ranks of w: make every mailbox at least data_bytes per
+   area (same value everywhere) and map the neighbours'; returns 1 when the
+   mailbox was (re)created, in which case epoch restarts at 0                 */
+int   xg_mbox_ensure(struct xg_world *w, struct xg_mbox *mb, const u32 *nbr, u32 nnbr, size_t data_bytes);
+void  xg_mbox_free(struct xg_world *w, struct xg_mbox *mb);
+
 /* host-side collectives over the rendezvous segment (np>1) */
 void  xg_host_barrier(struct xg_world *w);
 /* every rank contributes `bytes` bytes; out receives np*bytes, rank-major   */
@@ -171,6 +195,8 @@ void   xcu_ipc_export(void *handle64, void *devptr);
 void  *xcu_ipc_open(const void *handle64);
 void   xcu_ipc_close(void *p);
 void   xcu_device_uuid(int dev, char out16[16]);
+int    xcu_peer_ok(int dev, const char uuid16[16]);   /* can dev store into the device with that uuid? */
+void  *xcu_host_alloc_mapped(size_t bytes);
 
 /* a field as the kernels see it */
 struct xcu_field {
@@ -203,6 +229,24 @@ struct xcu_bnd {
   const u32 *ord;                /* all-reduce slot per boundary primary     */
   const unsigned char *pflag;    /* primary flagged?                          */
 };
+
+/* push transport: where the pack kernel stores (device tables of one handle,
+   one direction, one parity) and whom it signals                            */
+struct xcu_push {
+  const unsigned long long *base;  /* [neighbours] peer data area, as an address   */
+  const u32 *delta;                /* [neighbours] peer slot - my slot (mod 2^32)   */
+  const unsigned char *snb;        /* [slot entries] neighbour number of each entry */
+  const unsigned long long *sig;   /* [nsig] address of my flag in each neighbour   */
+  u32  nsig;                       /* 0: do not signal from this launch             */
+  u32  epoch;
+  u32 *counter;                    /* CTA completion counter in my mailbox          */
+};
+void xcu_bnd_pack_push(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
+                       int mode, int xdom, int xop, int transpose, unsigned bufvn,
+                       const struct xcu_push *pp);
+void xcu_push_signal(void *stream, const struct xcu_push *pp);
+void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, u32 epoch,
+                   double timeout_s, int *status);
 
 /* fused local gather(+init)+scatter over every group of m                  */
 void xcu_fused(void *stream, const struct xcu_csr *m, const struct xcu_field *f,

@@ -241,38 +241,102 @@ k_init_list(const u32 *__restrict__ list, u32 n, Fld<T, MODE> f)
   for (unsigned k = 0; k < f.vn; ++k) *f.at(i, k) = ident<T, OP>();
 }
 
-// boundary primaries: gather -> u[primary] and -> send slots
-template <typename T, int OP, int MODE>
+// boundary primaries: gather -> u[primary] and -> send slots.
+// PUSH: the send slots live in the neighbours' mailboxes; each value is stored
+// straight into the receiving GPU's memory over NVLink (the upc_memput of
+// pw_exec_sends, src/gs.upc:437-468, done by the thread that produced the
+// value), and the last CTA to finish raises this rank's flag in every
+// neighbour's mailbox (the "flag" put of the same function).
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{ asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{ unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__device__ __forceinline__ void push_signal_all(const xcu_push &pp)
+{
+  for (u32 i = 0; i < pp.nsig; ++i)
+    st_release_sys(reinterpret_cast<unsigned *>(pp.sig[i]), pp.epoch);
+}
+
+template <typename T, int OP, int MODE, bool PUSH>
 __global__ void __launch_bounds__(256)
 k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
-           unsigned bufvn, int allreduce)
+           unsigned bufvn, int allreduce, xcu_push pp)
 {
   u32 b = blockIdx.x * 256u + threadIdx.x;
-  if (b >= bd.nb) return;
-  u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
-  u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
-  group_counts(nall, nunf, transpose, nred, nwr);
-  const u32 *idx = bd.gidx + gb;
-  u32 prim = __ldg(idx);
-  const int sd = 1 ^ transpose;                 // send map (src/gs.upc:479)
-  u32 sb = 0, se = 0, ord = 0; bool contributes = true;
-  if (allreduce) {
-    ord = __ldg(bd.ord + b);
-    // map_to_buf (src/gs.upc:1059,1063): flagged primaries stay out unless transposed
-    contributes = transpose || !bd.pflag[b];
-  } else {
-    sb = __ldg(bd.soff[sd] + b); se = __ldg(bd.soff[sd] + b + 1);
-  }
-  for (unsigned k = 0; k < f.vn; ++k) {
-    T v = nred ? *f.at(prim, k) : ident<T, OP>();
-    for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, *f.at(__ldg(idx + j), k));
-    *f.at(prim, k) = v;
+  if (b < bd.nb) {
+    u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
+    u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
+    group_counts(nall, nunf, transpose, nred, nwr);
+    const u32 *idx = bd.gidx + gb;
+    u32 prim = __ldg(idx);
+    const int sd = 1 ^ transpose;                 // send map (src/gs.upc:479)
+    u32 sb = 0, se = 0, ord = 0; bool contributes = true;
     if (allreduce) {
-      if (contributes) sendbuf[(size_t)ord * bufvn + f.k0 + k] = v;
+      ord = __ldg(bd.ord + b);
+      // map_to_buf (src/gs.upc:1059,1063): flagged primaries stay out unless transposed
+      contributes = transpose || !bd.pflag[b];
     } else {
-      for (u32 s = sb; s < se; ++s)
-        sendbuf[(size_t)__ldg(bd.slot[sd] + s) * bufvn + f.k0 + k] = v;
+      sb = __ldg(bd.soff[sd] + b); se = __ldg(bd.soff[sd] + b + 1);
     }
+    for (unsigned k = 0; k < f.vn; ++k) {
+      T v = nred ? *f.at(prim, k) : ident<T, OP>();
+      for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, *f.at(__ldg(idx + j), k));
+      *f.at(prim, k) = v;
+      if (PUSH) {
+        for (u32 s = sb; s < se; ++s) {
+          const unsigned nbk = __ldg(pp.snb + s);
+          T *dst = reinterpret_cast<T *>(__ldg(pp.base + nbk));
+          const u32 slot = __ldg(bd.slot[sd] + s) + __ldg(pp.delta + nbk);
+          dst[(size_t)slot * bufvn + f.k0 + k] = v;
+        }
+      } else if (allreduce) {
+        if (contributes) sendbuf[(size_t)ord * bufvn + f.k0 + k] = v;
+      } else {
+        for (u32 s = sb; s < se; ++s)
+          sendbuf[(size_t)__ldg(bd.slot[sd] + s) * bufvn + f.k0 + k] = v;
+      }
+    }
+  }
+  if (PUSH && pp.nsig) {
+    __threadfence_system();                       // my peer stores are out
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(pp.counter, 1u);
+      if (done == gridDim.x - 1u) {               // every CTA's stores are out
+        *pp.counter = 0u;
+        __threadfence_system();
+        push_signal_all(pp);
+      }
+    }
+  }
+}
+
+// signal without data (a rank whose boundary groups send nothing this call)
+__global__ void k_push_signal(xcu_push pp)
+{
+  if (threadIdx.x == 0) { __threadfence_system(); push_signal_all(pp); }
+}
+
+// The receiving side of pw_exec_recvs' poll loop (src/gs.upc:409-435): one
+// thread per neighbour waits until that neighbour's flag in my own mailbox has
+// reached this call's epoch.  The flags are local memory written by the peer
+// over NVLink; the unpack kernel follows in stream order.  A bounded wait: a
+// peer that never arrives is reported through *status instead of hanging the
+// GPU.
+__global__ void k_push_wait(const unsigned *__restrict__ flags, const u32 *__restrict__ ranks,
+                            u32 n, u32 epoch, unsigned long long timeout_ns, int *status)
+{
+  const u32 t = threadIdx.x;
+  if (t >= n) return;
+  const unsigned *f = flags + ranks[t];
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { *status = 1 + (int)ranks[t]; break; }
+    __nanosleep(100);
   }
 }
 
@@ -453,11 +517,41 @@ void xcu_bnd_pack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, 
 {
   if (!b->nb) return;
   cudaStream_t st = (cudaStream_t)stream;
+  xcu_push none; memset(&none, 0, sizeof none);
 #define X(T, OP, MODE)                                                        \
-  k_bnd_pack<T, OP, MODE><<<blocks_for(b->nb), 256, 0, st>>>(                 \
-      *b, make_fld<T, MODE>(f), transpose, (T *)sendbuf, bufvn, allreduce)
+  k_bnd_pack<T, OP, MODE, false><<<blocks_for(b->nb), 256, 0, st>>>(          \
+      *b, make_fld<T, MODE>(f), transpose, (T *)sendbuf, bufvn, allreduce, none)
   FOR_ALL(X)
 #undef X
+  LAUNCHED();
+}
+
+void xcu_bnd_pack_push(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, int xdom,
+                       int xop, int transpose, unsigned bufvn, const xcu_push *pp)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!b->nb) { if (pp->nsig) xcu_push_signal(stream, pp); return; }
+#define X(T, OP, MODE)                                                        \
+  k_bnd_pack<T, OP, MODE, true><<<blocks_for(b->nb), 256, 0, st>>>(           \
+      *b, make_fld<T, MODE>(f), transpose, (T *)0, bufvn, 0, *pp)
+  FOR_ALL(X)
+#undef X
+  LAUNCHED();
+}
+
+void xcu_push_signal(void *stream, const xcu_push *pp)
+{
+  if (!pp->nsig) return;
+  k_push_signal<<<1, 32, 0, (cudaStream_t)stream>>>(*pp);
+  LAUNCHED();
+}
+
+void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, u32 epoch,
+                   double timeout_s, int *status)
+{
+  if (!n) return;
+  k_push_wait<<<1, (n + 31u) & ~31u, 0, (cudaStream_t)stream>>>(
+      flags, ranks, n, epoch, (unsigned long long)(timeout_s * 1e9), status);
   LAUNCHED();
 }
 
@@ -613,6 +707,30 @@ void xcu_device_uuid(int dev, char out16[16])
   cudaDeviceProp pr;
   CU(cudaGetDeviceProperties(&pr, dev));
   memcpy(out16, &pr.uuid, 16);
+}
+
+/* can `dev` store into the device whose uuid is given?  (same device: yes) */
+int xcu_peer_ok(int dev, const char uuid16[16])
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (memcmp(&pr.uuid, uuid16, 16) != 0) continue;
+    if (d == dev) return 1;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev, d) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return can;
+  }
+  return 0;   /* not visible to this process */
+}
+
+void *xcu_host_alloc_mapped(size_t bytes)
+{
+  void *p = 0;
+  CU(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable));
+  return p;
 }
 
 void *xcu_host_alloc(size_t bytes)

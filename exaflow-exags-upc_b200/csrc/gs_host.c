@@ -48,7 +48,12 @@ struct gs_data {
   void **pipe_ev;                     /* [2*chunks] events */
   u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
   struct xcu_bnd d_bnd;       /* boundary primaries */
-  void *d_bnd_mem[10];
+  void *d_bnd_mem[12];
+  /* push transport (pairwise over peer stores): this handle's mailbox and the
+     device tables that say where each neighbour's data area is */
+  struct xg_mbox mbox;
+  const unsigned char *d_snb[2];
+  u32 push_nnbmax;
   size_t handle_bytes;
 };
 
@@ -147,6 +152,56 @@ static void exchange_ipc_allreduce(struct gs_data *g, void *acc, size_t count, i
   xg_host_barrier(w);
 }
 
+/* Push transport: the exchange is part of the pack kernel (peer stores over
+   NVLink + a flag per neighbour), then a one-CTA wait on my own flags.  Device
+   tables, rebuilt whenever the mailbox is (re)created:
+     u64 base[parity][d][nnbmax]   neighbour k's data area for that parity
+     u64 sig[nsym]                 my flag inside each neighbour's mailbox
+     u32 delta[d][nnbmax]          neighbour's slot number - mine
+     u32 wait[nsym]                neighbour ranks (= flag numbers in my mailbox) */
+static void push_prepare(struct gs_data *g, size_t data_bytes)
+{
+  struct xg_world *w = g->w;
+  const struct xg_plan *pl = &g->plan;
+  struct xg_mbox *mb = &g->mbox;
+  if (!xg_mbox_ensure(w, mb, pl->sym_rank, pl->nsym, data_bytes) && mb->d_tab) return;
+  const u32 nm = pl->nnb[0] > pl->nnb[1] ? pl->nnb[0] : pl->nnb[1], M = nm ? nm : 1, ns = pl->nsym;
+  const size_t n64 = 4 * (size_t)M + ns, n32 = 2 * (size_t)M + ns;
+  u64 *t64 = xnew0(u64, n64 + (n32 + 1) / 2 + 1);
+  u32 *t32 = (u32 *)(t64 + n64);
+  const int me = xg_world_rank(w);
+  for (int par = 0; par < 2; ++par)
+    for (int d = 0; d < 2; ++d)
+      for (u32 k = 0; k < pl->nnb[d]; ++k)
+        t64[((size_t)par * 2 + d) * M + k] =
+          (u64)(uintptr_t)((char *)mb->peer[pl->nb_rank[d][k]] + XG_MBOX_HDR + (size_t)par * mb->data_bytes);
+  for (u32 i = 0; i < ns; ++i)
+    t64[4 * (size_t)M + i] = (u64)(uintptr_t)((char *)mb->peer[pl->sym_rank[i]] + 4 * (size_t)me);
+  for (int d = 0; d < 2; ++d)
+    for (u32 k = 0; k < pl->nnb[d]; ++k)
+      t32[(size_t)d * M + k] = pl->nb_peer_start[d][k] - pl->nb_start[d][k];
+  for (u32 i = 0; i < ns; ++i) t32[2 * (size_t)M + i] = pl->sym_rank[i];
+  if (mb->d_tab) { xcu_device_sync(); xcu_free(mb->d_tab); }
+  mb->d_tab = upload(t64, (n64 + (n32 + 1) / 2 + 1) * sizeof(u64));
+  xcu_device_sync();
+  free(t64);
+  g->push_nnbmax = M;
+}
+
+static double push_timeout(void)
+{
+  static double t = -1;
+  if (t < 0) { const char *v = getenv("EXAGS_PUSH_TIMEOUT_S"); t = v && atof(v) > 0 ? atof(v) : 20.0; }
+  return t;
+}
+
+static void push_check(struct gs_data *g, const char *when)
+{
+  int *st = xg_world_push_status(g->w);
+  if (st && *st)
+    xfail("gs: push exchange timed out waiting for rank %d (%s); is every rank calling gs collectively?", *st - 1, when);
+}
+
 /* ------------------------------------------------------------------ */
 /*  the operator                                                       */
 /* ------------------------------------------------------------------ */
@@ -163,15 +218,37 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
                        int xd, int xop, int transpose, void *stream)
 {
   struct xg_world *w = g->w;
-  const int multi = xg_world_np(w) > 1 && (g->plan.nb > 0 || g->method == gs_all_reduce);
   const int allred = g->method == gs_all_reduce;
+  const int push = xg_world_push(w) && !allred;
+  /* the pull and push transports have collective steps (host barriers, mailbox
+     growth): there a rank takes part whenever any rank has something to send */
+  const int multi = xg_world_np(w) > 1 &&
+    (allred || ((push || xg_world_ipc(w)) ? g->plan.max_total > 0 : g->plan.nb > 0));
   const unsigned esz = xg_dom_bytes(xd);
   void *scomm = 0, *sendbuf = 0, *recvbuf = 0;
+  struct xcu_push pp; memset(&pp, 0, sizeof pp);
+  const u32 *push_wait = 0;
 
   if (multi) {
     const struct xg_plan *pl = &g->plan;
     scomm = xg_world_stream(w, 1);
-    if (xg_world_ipc(w)) {
+    if (push) {
+      push_check(g, "before this call");
+      push_prepare(g, (size_t)pl->max_total * vn * esz);
+      struct xg_mbox *mb = &g->mbox;
+      const u32 M = g->push_nnbmax, epoch = ++mb->epoch, par = epoch & 1u;
+      const int sd = 1 ^ transpose;
+      const u64 *t64 = (const u64 *)mb->d_tab;
+      const u32 *t32 = (const u32 *)(t64 + 4 * (size_t)M + pl->nsym);
+      pp.base = (const unsigned long long *)(t64 + ((size_t)par * 2 + sd) * M);
+      pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
+      pp.delta = t32 + (size_t)sd * M;
+      pp.snb = g->d_snb[sd];
+      pp.nsig = pl->nsym; pp.epoch = epoch;
+      pp.counter = (u32 *)((char *)mb->mine + 512);
+      push_wait = t32 + 2 * (size_t)M;
+      recvbuf = (char *)mb->mine + XG_MBOX_HDR + (size_t)par * mb->data_bytes;
+    } else if (xg_world_ipc(w)) {
       sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
       recvbuf = xg_world_scratch(w, allred ? 3 : 1, (size_t)pl->max_total * vn * esz);
     } else if (allred) {
@@ -195,7 +272,12 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
       f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = (mode == XM_MANY) ? k0 : 0;
       if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
       else f.p[0] = ptrs[0];
-      xcu_bnd_pack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, sendbuf, vn, allred);
+      if (push) {
+        struct xcu_push p1 = pp;
+        if (k0 + step < vn) p1.nsig = 0;        /* only the last launch signals */
+        xcu_bnd_pack_push(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, vn, &p1);
+      } else
+        xcu_bnd_pack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, sendbuf, vn, allred);
     }
   /* interior: fused gather-scatter on the caller's stream */
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
@@ -208,7 +290,10 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
   if (multi) {
-    if (xg_world_ipc(w)) {
+    if (push)
+      xcu_push_wait(scomm, (const u32 *)g->mbox.mine, push_wait, g->plan.nsym, pp.epoch,
+                    push_timeout(), xg_world_push_status(w));
+    else if (xg_world_ipc(w)) {
       if (allred) exchange_ipc_allreduce(g, recvbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
       else exchange_ipc_pairwise(g, vn, xd, transpose, recvbuf, scomm);
     } else if (allred) xg_nccl_allreduce(w, sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
@@ -336,7 +421,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
 
   if (!host) {
     gs_enqueue(g, ptrs, mode, vn, xd, op, (int)transpose, stream);
-    if (blocking) xcu_stream_sync(stream);
+    if (blocking) { xcu_stream_sync(stream); push_check(g, "during this call"); }
     free(ptrs);
     return;
   }
@@ -362,6 +447,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   if (mode == XM_MANY) for (unsigned k = 0; k < vn; ++k) xcu_d2h(ptrs[k], dptr[k], each, stream);
   else xcu_d2h(u, stage, total, stream);
   xcu_stream_sync(stream);
+  push_check(g, "during this call");
   free(dptr); free(ptrs);
 }
 
@@ -479,6 +565,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
       }
       UP(d->ord, pl->ord, nb);
       UP(d->pflag, pl->pflag, nb);
+      for (int dd = 0; dd < 2; ++dd) UP(g->d_snb[dd], pl->snb[dd], pl->total[dd] ? pl->total[dd] : 1);
 #undef UP
     }
     xcu_device_sync();
@@ -501,12 +588,37 @@ static double time_exchange(struct gs_data *g, int method)
   void *s = xg_world_stream(w, 1);
   size_t nsend = method == gs_all_reduce ? (size_t)pl->total_shared : pl->total[1];
   size_t nrecv = method == gs_all_reduce ? 0 : pl->total[0];
-  void *sb = xg_world_scratch(w, 0, nsend * 8), *rb = xg_world_scratch(w, 1, nrecv * 8);
+  if (method == gs_all_reduce && xg_world_ipc(w)) nrecv = nsend;
+  void *sb = xg_world_scratch(w, 0, nsend * 8);
+  void *rb = xg_world_scratch(w, method == gs_all_reduce && xg_world_ipc(w) ? 3 : 1, nrecv * 8);
   xcu_memset(sb, 0, nsend * 8, s);
   double t0 = 0, t1 = 0;
+  const int push = xg_world_push(w) && method != gs_all_reduce;
+  if (xg_world_ipc(w) && !push) sb = xg_ipc_buffer(w, (size_t)pl->max_total * 8);
   for (int it = 0; it < 12; ++it) {
     if (it == 2) { xcu_stream_sync(s); xg_host_barrier(w); exags_comm_time(&t0); }
-    if (method == gs_all_reduce) xg_nccl_allreduce(w, sb, nsend, XD_F64, XO_ADD, s);
+    if (push) {
+      /* the transport alone: copy each neighbour's segment into its mailbox,
+         raise the flags, wait for mine */
+      push_prepare(g, (size_t)pl->max_total * 8);
+      struct xg_mbox *mb = &g->mbox;
+      const u32 M = g->push_nnbmax, epoch = ++mb->epoch, par = epoch & 1u;
+      const u64 *t64 = (const u64 *)mb->d_tab;
+      struct xcu_push pp; memset(&pp, 0, sizeof pp);
+      pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
+      pp.nsig = pl->nsym; pp.epoch = epoch;
+      for (u32 k = 0; k < pl->nnb[1]; ++k)
+        xcu_d2d((char *)mb->peer[pl->nb_rank[1][k]] + XG_MBOX_HDR + (size_t)par * mb->data_bytes + (size_t)pl->nb_peer_start[1][k] * 8,
+                (const char *)sb + (size_t)pl->nb_start[1][k] * 8, (size_t)pl->nb_size[1][k] * 8, s);
+      xcu_push_signal(s, &pp);
+      xcu_push_wait(s, (const u32 *)mb->mine, (const u32 *)(t64 + 4 * (size_t)M + pl->nsym) + 2 * (size_t)M,
+                    pl->nsym, epoch, push_timeout(), xg_world_push_status(w));
+    }
+    else if (xg_world_ipc(w)) {
+      if (method == gs_all_reduce) exchange_ipc_allreduce(g, rb, nsend, XD_F64, XO_ADD, s);
+      else exchange_ipc_pairwise(g, 1, XD_F64, 0, rb, s);
+    }
+    else if (method == gs_all_reduce) xg_nccl_allreduce(w, sb, nsend, XD_F64, XO_ADD, s);
     else exchange_pairwise(g, 1, XD_F64, 0, sb, rb, s);
   }
   xcu_stream_sync(s);
@@ -635,7 +747,8 @@ void exags_gs_free(struct gs_data *g)
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
     xcu_free(g->d_fs);
     for (int m = 0; m < 2; ++m) xcu_free(g->d_sell_mem[m]);
-    for (int m = 0; m < 10; ++m) xcu_free(g->d_bnd_mem[m]);
+    for (int m = 0; m < 12; ++m) xcu_free(g->d_bnd_mem[m]);
+    xg_mbox_free(g->w, &g->mbox);
   }
   xg_hmap_free(&g->hall);
   free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);

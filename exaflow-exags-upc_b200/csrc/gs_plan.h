@@ -38,6 +38,11 @@ struct xg_plan {
      count of any rank/direction (uniform buffer sizing) */
   u32 *nb_peer_start[2];
   u64  max_total;
+  /* for the push transport: neighbour number (index into nb_rank[d]) of each
+     entry of slot[d], and the union of both directions' neighbours -- the
+     same set on either side of every pair, so signals and waits match up   */
+  unsigned char *snb[2];
+  u32  nsym, *sym_rank;
 };
 
 void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w);

@@ -206,7 +206,9 @@ void xg_plan_free(struct xg_plan *pl)
   for (int d = 0; d < 2; ++d) {
     free(pl->soff[d]); free(pl->slot[d]);
     free(pl->nb_rank[d]); free(pl->nb_start[d]); free(pl->nb_size[d]); free(pl->nb_peer_start[d]);
+    free(pl->snb[d]);
   }
+  free(pl->sym_rank);
   free(pl->ord); free(pl->pflag);
   memset(pl, 0, sizeof *pl);
 }
@@ -293,6 +295,27 @@ void xg_plan_build(struct xg_plan *pl, struct xg_shared *sh, const struct xg_top
     for (size_t k = 0; k < ns; ++k)         /* rows are in (p,id) order */
       if (bi[k] != XG_NONE) pl->slot[d][fill[bof[k]]++] = bi[k];
     free(fill); free(bi);
+    /* neighbour number of each slot-list entry: a neighbour's slots are one
+       contiguous range of the numbering */
+    pl->snb[d] = xnew(unsigned char, count ? count : 1);
+    for (u32 s = 0; s < count; ++s) {
+      u32 v = pl->slot[d][s], lo = 0, hi = nn;
+      while (hi - lo > 1) { u32 mid = (lo + hi) / 2; if (pl->nb_start[d][mid] <= v) lo = mid; else hi = mid; }
+      pl->snb[d][s] = (unsigned char)lo;
+    }
+  }
+  /* union of both directions' neighbours, ascending */
+  {
+    u32 a = 0, b = 0, o = 0;
+    pl->sym_rank = xnew(u32, (size_t)pl->nnb[0] + pl->nnb[1] + 1);
+    while (a < pl->nnb[0] || b < pl->nnb[1]) {
+      u32 ra = a < pl->nnb[0] ? pl->nb_rank[0][a] : XG_NONE, rb = b < pl->nnb[1] ? pl->nb_rank[1][b] : XG_NONE;
+      u32 r = ra < rb ? ra : rb;
+      pl->sym_rank[o++] = r;
+      if (ra == r) ++a;
+      if (rb == r) ++b;
+    }
+    pl->nsym = o;
   }
   free(bof); free(perm);
   (void)nbits64;

@@ -1,7 +1,9 @@
-"""Multi-rank parity on real GPUs: one process per GPU, NCCL halo exchange,
-every domain x op x transpose x mode against the oracle (rank 0 checks).
-Needs at least 2 devices; the 1-GPU box skips these and relies on the CPU
-multi-rank setup tests plus the single-device exchange test below."""
+"""Multi-rank parity on real GPUs: one process per GPU, halo exchange by peer
+stores over NVLink (push, the default) and by NCCL send/recv, every domain x
+op x transpose x mode against the oracle (rank 0 checks).  Needs at least 2
+devices; the 1-GPU box skips these and relies on the CPU multi-rank setup
+tests plus the single-device exchange tests below (pull and push transports
+between processes sharing GPU 0)."""
 import pytest
 
 from mp_launch import run_ranks
@@ -17,10 +19,22 @@ def _ndev():
 @pytest.mark.parametrize("np_,case,method", [(2, "slab", 1), (2, "fixture", 1), (2, "random", 1),
                                              (2, "slab", 3), (2, "empty", 1), (4, "blocks", 1),
                                              (4, "blocks", 3), (8, "blocks", 1)])
-def test_multirank_exec_nccl(built, np_, case, method):
+@pytest.mark.parametrize("transport", ["push", "nccl"])
+def test_multirank_exec_nccl(built, np_, case, method, transport):
     if _ndev() < np_:
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
-    codes, outs = run_ranks(np_, [case, "exec", 0, method], timeout=600)
+    codes, outs = run_ranks(np_, [case, "exec", 0, method], timeout=600,
+                            extra_env={"EXAGS_EXCHANGE": transport})
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks"), (8, "blocks"), (3, "empty")])
+def test_multirank_auto_method(built, np_, case):
+    """gs_auto (what fgs_setup uses): times the transports like auto_setup,
+    src/gs.upc:1113-1156, and must give the same results whichever it keeps."""
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "exec", 0, 0], timeout=600)
     assert all(c == 0 for c in codes), "\n".join(outs)
 
 
@@ -44,4 +58,19 @@ def test_multirank_exec_one_gpu(built, np_, case, method, unique):
         pytest.skip("needs a GPU")
     codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0"})
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case,method,unique", [(2, "slab", 1, 0), (3, "random", 1, 0), (4, "blocks", 1, 0),
+                                                    (2, "fixture", 1, 0), (2, "slab", 1, 1), (3, "empty", 1, 0),
+                                                    (2, "slab", 0, 0)])
+def test_multirank_exec_one_gpu_push(built, np_, case, method, unique):
+    """The push transport (pack kernel stores into the neighbours' CUDA-IPC
+    mapped mailboxes, flag per neighbour, one-CTA wait) between processes that
+    share GPU 0: the kernels of the ranks time-slice, so this is slow but it
+    runs the same code as NVLink peers do."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": "push"})
     assert all(c == 0 for c in codes), "\n".join(outs)
