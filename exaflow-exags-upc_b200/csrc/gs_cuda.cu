@@ -192,15 +192,12 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 // KU = components handled per pass: 1 for plain fields; 3 for vec/many so the
 // loads of all three components of a velocity field are in flight together
 // (BASELINE config 3) and the index block is read once for all of them.
-template <typename T, int OP, int MODE, int KU, int MINB>
-__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
-k_fused_sell(xcu_sell m, Fld<T, MODE> f)
+// one block of one lane: 8 predicated loads per component, segmented scan, 8
+// predicated stores
+template <typename T, int OP, int MODE, int KU>
+__device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
+                                          const unsigned start)
 {
-  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
-  const unsigned lane = threadIdx.x & 31u;
-  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
-  const uint4 a = __ldg(p), b = __ldg(p + 1);
-  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   for (unsigned k0 = 0; k0 < f.vn; k0 += KU) {
     T x[KU][8];
@@ -228,6 +225,63 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f)
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) *f.at(id[j], k0 + kk) = x[kk][j];
       }
+  }
+}
+
+// index stream: read once, never reused -- keep it out of L1 and first to go in L2
+// (sm_100 has 256-bit global loads: a lane's 8 slots are one instruction)
+__device__ __forceinline__ void ld_stream8(const u32 *p, uint4 &a, uint4 &b)
+{
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
+template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM = false>
+__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
+k_fused_sell(xcu_sell m, Fld<T, MODE> f)
+{
+  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
+  uint4 a, b;
+  if (STREAM) ld_stream8(reinterpret_cast<const u32 *>(p), a, b);
+  else { a = __ldg(p); b = __ldg(p + 1); }
+  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
+  sell_lane<T, OP, MODE, KU>(f, a, b, start);
+}
+
+// Persistent form: a fixed grid (a multiple of the SM count) walks the windows
+// with stride gridDim.x and each warp fetches the indices of its next block
+// before it touches the field for the current one, so the index -> field load
+// chain of consecutive blocks overlaps instead of adding up.
+template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM>
+__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
+k_fused_sell_pp(xcu_sell m, Fld<T, MODE> f)
+{
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 nwin = m.nblock / (u32)XG_SELL_WB;
+  u32 win = blockIdx.x;
+  if (win >= nwin) return;
+  size_t c = (size_t)win * XG_SELL_WB + warp;
+  const u32 *p = m.idx + (c * 32u + lane) * 8u;
+  uint4 a, b;
+  if (STREAM) ld_stream8(p, a, b);
+  else { a = __ldg(reinterpret_cast<const uint4 *>(p)); b = __ldg(reinterpret_cast<const uint4 *>(p) + 1); }
+  unsigned start = __ldg(m.mask + c * 32u + lane);
+  for (;;) {
+    const u32 nxt = win + gridDim.x;
+    uint4 na = a, nb = b; unsigned ns = start;
+    if (nxt < nwin) {
+      c = (size_t)nxt * XG_SELL_WB + warp;
+      p = m.idx + (c * 32u + lane) * 8u;
+      if (STREAM) ld_stream8(p, na, nb);
+      else { na = __ldg(reinterpret_cast<const uint4 *>(p)); nb = __ldg(reinterpret_cast<const uint4 *>(p) + 1); }
+      ns = __ldg(m.mask + c * 32u + lane);
+    }
+    sell_lane<T, OP, MODE, KU>(f, a, b, start);
+    if (nxt >= nwin) break;
+    win = nxt; a = na; b = nb; start = ns;
   }
 }
 
@@ -263,8 +317,7 @@ __global__ void __launch_bounds__(256)
 k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
            unsigned bufvn, int allreduce, xcu_push pp)
 {
-  u32 b = blockIdx.x * 256u + threadIdx.x;
-  if (b < bd.nb) {
+  for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
     u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
     u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
     group_counts(nall, nunf, transpose, nred, nwr);
@@ -346,31 +399,31 @@ __global__ void __launch_bounds__(256)
 k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ recvbuf,
              unsigned bufvn, int allreduce)
 {
-  u32 b = blockIdx.x * 256u + threadIdx.x;
-  if (b >= bd.nb) return;
-  u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
-  u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
-  group_counts(nall, nunf, transpose, nred, nwr);
-  const u32 *idx = bd.gidx + gb;
-  u32 prim = __ldg(idx);
-  const int rd = 0 ^ transpose;                 // recv map (src/gs.upc:479)
-  u32 rb = 0, re = 0, ord = 0; bool takes = true;
-  if (allreduce) {
-    ord = __ldg(bd.ord + b);
-    // map_from_buf (src/gs.upc:1060,1064)
-    takes = !transpose || !bd.pflag[b];
-  } else {
-    rb = __ldg(bd.soff[rd] + b); re = __ldg(bd.soff[rd] + b + 1);
-  }
-  for (unsigned k = 0; k < f.vn; ++k) {
-    T v = *f.at(prim, k);
+  for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
+    u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
+    u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
+    group_counts(nall, nunf, transpose, nred, nwr);
+    const u32 *idx = bd.gidx + gb;
+    u32 prim = __ldg(idx);
+    const int rd = 0 ^ transpose;                 // recv map (src/gs.upc:479)
+    u32 rb = 0, re = 0, ord = 0; bool takes = true;
     if (allreduce) {
-      if (takes) v = recvbuf[(size_t)ord * bufvn + f.k0 + k];
+      ord = __ldg(bd.ord + b);
+      // map_from_buf (src/gs.upc:1060,1064)
+      takes = !transpose || !bd.pflag[b];
     } else {
-      for (u32 s = rb; s < re; ++s)
-        v = apply<T, OP>(v, recvbuf[(size_t)__ldg(bd.slot[rd] + s) * bufvn + f.k0 + k]);
+      rb = __ldg(bd.soff[rd] + b); re = __ldg(bd.soff[rd] + b + 1);
     }
-    for (u32 j = 0; j < nwr; ++j) *f.at(__ldg(idx + j), k) = v;
+    for (unsigned k = 0; k < f.vn; ++k) {
+      T v = *f.at(prim, k);
+      if (allreduce) {
+        if (takes) v = recvbuf[(size_t)ord * bufvn + f.k0 + k];
+      } else {
+        for (u32 s = rb; s < re; ++s)
+          v = apply<T, OP>(v, recvbuf[(size_t)__ldg(bd.slot[rd] + s) * bufvn + f.k0 + k]);
+      }
+      for (u32 j = 0; j < nwr; ++j) *f.at(__ldg(idx + j), k) = v;
+    }
   }
 }
 
@@ -426,6 +479,23 @@ k_csr_scatter(xcu_csr m, FldR<T> out, FldR<T> in)
 // ---------------------------------------------------------------------------
 static inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255u) / 256u); }
 
+/* Boundary kernels run on the high-priority stream beside the interior
+   kernel and have its whole duration to finish.  A full-width grid of them
+   would take every SM away from the bandwidth-bound interior kernel for the
+   length of their dependent-load chains, so they get one CTA per SM (grid-
+   stride) until the boundary is big enough to need more: at most ~16 groups
+   per thread. */
+static inline unsigned bnd_blocks(size_t nb)
+{
+  unsigned want = blocks_for(nb), narrow = (unsigned)((nb + 4095u) / 4096u);
+  static int sm = 0, wide = -1;
+  if (wide < 0) { const char *v = getenv("EXAGS_BND_WIDE"); wide = v ? atoi(v) : 0; }
+  if (wide) return want;
+  if (!sm) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, d); if (sm <= 0) sm = 148; }
+  if (narrow < (unsigned)sm) narrow = (unsigned)sm;
+  return narrow < want ? narrow : want;
+}
+
 #define FOR_OP(T, MODE, X)                                                    \
   switch (xop) {                                                              \
     case XO_ADD: X(T, XO_ADD, MODE); break;                                   \
@@ -477,15 +547,39 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = m->nblock / XG_SELL_WB;
   const unsigned nthr = 32 * XG_SELL_WB;
+  static int variant = -1, ctas = 0;
+  if (variant < 0) {
+    const char *v = getenv("EXAGS_SELL_VARIANT"); variant = v ? atoi(v) : 0;
+    v = getenv("EXAGS_SELL_CTAS"); ctas = v ? atoi(v) : 0;
+  }
   if (mode == XM_PLAIN || f->vn == 1) {
     /* one component: a vec/many field with vn == 1 is addressed like a plain one */
     xcu_field f1 = *f;
     f1.vn = 1; f1.tuple = 1;
     mode = XM_PLAIN;
+    if (variant == 0) {
 #define X(T, OP, MODE)                                                        \
   k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
     FOR_DOM(XM_PLAIN, X)
 #undef X
+    } else {
+      /* tuning variants: persistent grid of 148*ctas CTAs */
+      const unsigned per = ctas > 0 ? (unsigned)ctas : (variant == 3 || variant == 4 ? 4u : 5u);
+      unsigned pg = 148u * per; if (pg > grid) pg = grid;
+#define X(T, OP, MODE)                                                        \
+  switch (variant) {                                                          \
+    case 1: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 5, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+    case 2: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 5, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break;  \
+    case 3: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 4, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+    case 4: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 4, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break;  \
+    case 5: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 6, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+    case 7: k_fused_sell<T, OP, XM_PLAIN, 1, 6, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+    case 8: k_fused_sell<T, OP, XM_PLAIN, 1, 5, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+    default: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 6, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
+  }
+    FOR_DOM(XM_PLAIN, X)
+#undef X
+    }
   } else if (mode == XM_VEC) {
 #define X(T, OP, MODE)                                                        \
   k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f))
@@ -519,7 +613,7 @@ void xcu_bnd_pack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, 
   cudaStream_t st = (cudaStream_t)stream;
   xcu_push none; memset(&none, 0, sizeof none);
 #define X(T, OP, MODE)                                                        \
-  k_bnd_pack<T, OP, MODE, false><<<blocks_for(b->nb), 256, 0, st>>>(          \
+  k_bnd_pack<T, OP, MODE, false><<<bnd_blocks(b->nb), 256, 0, st>>>(          \
       *b, make_fld<T, MODE>(f), transpose, (T *)sendbuf, bufvn, allreduce, none)
   FOR_ALL(X)
 #undef X
@@ -532,7 +626,7 @@ void xcu_bnd_pack_push(void *stream, const xcu_bnd *b, const xcu_field *f, int m
   cudaStream_t st = (cudaStream_t)stream;
   if (!b->nb) { if (pp->nsig) xcu_push_signal(stream, pp); return; }
 #define X(T, OP, MODE)                                                        \
-  k_bnd_pack<T, OP, MODE, true><<<blocks_for(b->nb), 256, 0, st>>>(           \
+  k_bnd_pack<T, OP, MODE, true><<<bnd_blocks(b->nb), 256, 0, st>>>(           \
       *b, make_fld<T, MODE>(f), transpose, (T *)0, bufvn, 0, *pp)
   FOR_ALL(X)
 #undef X
@@ -561,7 +655,7 @@ void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode
   if (!b->nb) return;
   cudaStream_t st = (cudaStream_t)stream;
 #define X(T, OP, MODE)                                                        \
-  k_bnd_unpack<T, OP, MODE><<<blocks_for(b->nb), 256, 0, st>>>(               \
+  k_bnd_unpack<T, OP, MODE><<<bnd_blocks(b->nb), 256, 0, st>>>(               \
       *b, make_fld<T, MODE>(f), transpose, (const T *)recvbuf, bufvn, allreduce)
   FOR_ALL(X)
 #undef X

@@ -42,6 +42,8 @@ struct gs_data {
   size_t sell_idx_entries;
   /* pipelined host-pointer path (np == 1, symmetric map): chunk schedule */
   u32 nwin, *win_min, *win_max;       /* host copies from the sliced layout */
+  u32 *h_bidx; size_t h_nbidx;        /* boundary groups' member indices (np > 1) */
+  unsigned char *pipe_bnd;            /* [chunks] chunk holds a boundary member: final only after the unpack */
   unsigned pipe_chunks;               /* 0: not available */
   u32 *pipe_run;                      /* [chunks] windows runnable once chunks 0..k are on the device */
   u32 *pipe_out_wave;                 /* [chunks] wave after which chunk j is final */
@@ -212,99 +214,128 @@ static void check_dom_op(int dom, int op, int *xd, const char *who)
   if (op < 0 || op >= XO_N) xfail("%s: op %d not in valid range", who, op);
 }
 
+/* ---- boundary half of one call (np > 1): pack [+ push] ... exchange, unpack ---- */
+struct bnd_ctx {
+  int active, allred, push;
+  void *sendbuf, *recvbuf;
+  struct xcu_push pp;
+  const u32 *push_wait;
+};
+
+static void field_of(struct xcu_field *f, void *const *ptrs, int mode, unsigned vn, unsigned k0,
+                     unsigned step, int buffer_side)
+{
+  memset(f, 0, sizeof *f);
+  f->vn = (vn - k0 < step) ? vn - k0 : step; f->tuple = vn;
+  f->k0 = (buffer_side && mode == XM_MANY) ? k0 : 0;     /* component offset inside the [slot][vn] buffers */
+  if (mode == XM_MANY) for (unsigned k = 0; k < f->vn; ++k) f->p[k] = ptrs[k0 + k];
+  else f->p[0] = ptrs[0];
+}
+
+/* Decide whether this rank takes part in an exchange and get the buffers.
+   The pull and push transports have collective steps (host barriers, mailbox
+   growth): there a rank takes part whenever any rank has something to send. */
+static void bnd_prepare(struct gs_data *g, struct bnd_ctx *c, unsigned vn, int xd, int transpose)
+{
+  struct xg_world *w = g->w;
+  const struct xg_plan *pl = &g->plan;
+  const unsigned esz = xg_dom_bytes(xd);
+  memset(c, 0, sizeof *c);
+  c->allred = g->method == gs_all_reduce;
+  c->push = xg_world_push(w) && !c->allred;
+  c->active = xg_world_np(w) > 1 &&
+    (c->allred || ((c->push || xg_world_ipc(w)) ? pl->max_total > 0 : pl->nb > 0));
+  if (!c->active) return;
+  if (c->push) {
+    push_check(g, "before this call");
+    push_prepare(g, (size_t)pl->max_total * vn * esz);
+    struct xg_mbox *mb = &g->mbox;
+    const u32 M = g->push_nnbmax, epoch = ++mb->epoch, par = epoch & 1u;
+    const int sd = 1 ^ transpose;
+    const u64 *t64 = (const u64 *)mb->d_tab;
+    const u32 *t32 = (const u32 *)(t64 + 4 * (size_t)M + pl->nsym);
+    c->pp.base = (const unsigned long long *)(t64 + ((size_t)par * 2 + sd) * M);
+    c->pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
+    c->pp.delta = t32 + (size_t)sd * M;
+    c->pp.snb = g->d_snb[sd];
+    c->pp.nsig = pl->nsym; c->pp.epoch = epoch;
+    c->pp.counter = (u32 *)((char *)mb->mine + 512);
+    c->push_wait = t32 + 2 * (size_t)M;
+    c->recvbuf = (char *)mb->mine + XG_MBOX_HDR + (size_t)par * mb->data_bytes;
+  } else if (xg_world_ipc(w)) {
+    c->sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
+    c->recvbuf = xg_world_scratch(w, c->allred ? 3 : 1, (size_t)pl->max_total * vn * esz);
+  } else if (c->allred) {
+    c->sendbuf = xg_world_scratch(w, 0, (size_t)pl->total_shared * vn * esz);
+    c->recvbuf = c->sendbuf;
+  } else {
+    c->sendbuf = xg_world_scratch(w, 0, (size_t)pl->total[1 ^ transpose] * vn * esz);
+    c->recvbuf = xg_world_scratch(w, 1, (size_t)pl->total[0 ^ transpose] * vn * esz);
+  }
+}
+
+/* gather + pack (with the push transport this is also the send) */
+static void bnd_pack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, int mode, unsigned vn,
+                     int xd, int xop, int transpose, void *scomm)
+{
+  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
+  if (c->allred) xcu_fill_identity(scomm, c->sendbuf, (size_t)g->plan.total_shared * vn, xd, xop);
+  for (unsigned k0 = 0; k0 < vn; k0 += step) {
+    struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
+    if (c->push) {
+      struct xcu_push p1 = c->pp;
+      if (k0 + step < vn) p1.nsig = 0;        /* only the last launch signals */
+      xcu_bnd_pack_push(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, vn, &p1);
+    } else
+      xcu_bnd_pack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, c->sendbuf, vn, c->allred);
+  }
+}
+
+/* exchange (or wait for the neighbours' stores) + unpack and scatter */
+static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, int mode, unsigned vn,
+                       int xd, int xop, int transpose, void *scomm)
+{
+  struct xg_world *w = g->w;
+  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
+  if (c->push)
+    xcu_push_wait(scomm, (const u32 *)g->mbox.mine, c->push_wait, g->plan.nsym, c->pp.epoch,
+                  push_timeout(), xg_world_push_status(w));
+  else if (xg_world_ipc(w)) {
+    if (c->allred) exchange_ipc_allreduce(g, c->recvbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
+    else exchange_ipc_pairwise(g, vn, xd, transpose, c->recvbuf, scomm);
+  } else if (c->allred) xg_nccl_allreduce(w, c->sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
+  else exchange_pairwise(g, vn, xd, transpose, c->sendbuf, c->recvbuf, scomm);
+  for (unsigned k0 = 0; k0 < vn; k0 += step) {
+    struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
+    xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, c->recvbuf, vn, c->allred);
+  }
+}
+
 /* Enqueue one gs on device-resident data.  ptrs: vn device pointers for
    mode many, else ptrs[0].  Work is ordered on `stream`.                   */
 static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
                        int xd, int xop, int transpose, void *stream)
 {
   struct xg_world *w = g->w;
-  const int allred = g->method == gs_all_reduce;
-  const int push = xg_world_push(w) && !allred;
-  /* the pull and push transports have collective steps (host barriers, mailbox
-     growth): there a rank takes part whenever any rank has something to send */
-  const int multi = xg_world_np(w) > 1 &&
-    (allred || ((push || xg_world_ipc(w)) ? g->plan.max_total > 0 : g->plan.nb > 0));
-  const unsigned esz = xg_dom_bytes(xd);
-  void *scomm = 0, *sendbuf = 0, *recvbuf = 0;
-  struct xcu_push pp; memset(&pp, 0, sizeof pp);
-  const u32 *push_wait = 0;
-
-  if (multi) {
-    const struct xg_plan *pl = &g->plan;
-    scomm = xg_world_stream(w, 1);
-    if (push) {
-      push_check(g, "before this call");
-      push_prepare(g, (size_t)pl->max_total * vn * esz);
-      struct xg_mbox *mb = &g->mbox;
-      const u32 M = g->push_nnbmax, epoch = ++mb->epoch, par = epoch & 1u;
-      const int sd = 1 ^ transpose;
-      const u64 *t64 = (const u64 *)mb->d_tab;
-      const u32 *t32 = (const u32 *)(t64 + 4 * (size_t)M + pl->nsym);
-      pp.base = (const unsigned long long *)(t64 + ((size_t)par * 2 + sd) * M);
-      pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
-      pp.delta = t32 + (size_t)sd * M;
-      pp.snb = g->d_snb[sd];
-      pp.nsig = pl->nsym; pp.epoch = epoch;
-      pp.counter = (u32 *)((char *)mb->mine + 512);
-      push_wait = t32 + 2 * (size_t)M;
-      recvbuf = (char *)mb->mine + XG_MBOX_HDR + (size_t)par * mb->data_bytes;
-    } else if (xg_world_ipc(w)) {
-      sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
-      recvbuf = xg_world_scratch(w, allred ? 3 : 1, (size_t)pl->max_total * vn * esz);
-    } else if (allred) {
-      sendbuf = xg_world_scratch(w, 0, (size_t)pl->total_shared * vn * esz);
-      recvbuf = sendbuf;
-    } else {
-      sendbuf = xg_world_scratch(w, 0, (size_t)pl->total[1 ^ transpose] * vn * esz);
-      recvbuf = xg_world_scratch(w, 1, (size_t)pl->total[0 ^ transpose] * vn * esz);
-    }
+  struct bnd_ctx bc;
+  void *scomm = xg_world_stream(w, 1);
+  bnd_prepare(g, &bc, vn, xd, transpose);
+  if (bc.active) {
     /* fork: boundary stream starts after whatever precedes us on `stream` */
     xcu_event_record(xg_world_event(w, 0), stream);
     xcu_stream_wait_event(scomm, xg_world_event(w, 0));
-    if (allred) xcu_fill_identity(scomm, sendbuf, (size_t)pl->total_shared * vn, xd, xop);
+    bnd_pack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
   }
-
-  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
-  /* boundary: gather + pack */
-  if (multi)
-    for (unsigned k0 = 0; k0 < vn; k0 += step) {
-      struct xcu_field f; memset(&f, 0, sizeof f);
-      f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = (mode == XM_MANY) ? k0 : 0;
-      if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
-      else f.p[0] = ptrs[0];
-      if (push) {
-        struct xcu_push p1 = pp;
-        if (k0 + step < vn) p1.nsig = 0;        /* only the last launch signals */
-        xcu_bnd_pack_push(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, vn, &p1);
-      } else
-        xcu_bnd_pack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, sendbuf, vn, allred);
-    }
   /* interior: fused gather-scatter on the caller's stream */
+  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
-    struct xcu_field f; memset(&f, 0, sizeof f);
-    f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = 0;
-    if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
-    else f.p[0] = ptrs[0];
+    struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
     if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
-  if (multi) {
-    if (push)
-      xcu_push_wait(scomm, (const u32 *)g->mbox.mine, push_wait, g->plan.nsym, pp.epoch,
-                    push_timeout(), xg_world_push_status(w));
-    else if (xg_world_ipc(w)) {
-      if (allred) exchange_ipc_allreduce(g, recvbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
-      else exchange_ipc_pairwise(g, vn, xd, transpose, recvbuf, scomm);
-    } else if (allred) xg_nccl_allreduce(w, sendbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
-    else exchange_pairwise(g, vn, xd, transpose, sendbuf, recvbuf, scomm);
-    for (unsigned k0 = 0; k0 < vn; k0 += step) {
-      struct xcu_field f; memset(&f, 0, sizeof f);
-      f.vn = (vn - k0 < step) ? vn - k0 : step; f.tuple = vn; f.k0 = (mode == XM_MANY) ? k0 : 0;
-      if (mode == XM_MANY) for (unsigned k = 0; k < f.vn; ++k) f.p[k] = ptrs[k0 + k];
-      else f.p[0] = ptrs[0];
-      xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, recvbuf, vn, allred);
-    }
+  if (bc.active) {
+    bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
     /* join */
     xcu_event_record(xg_world_event(w, 1), scomm);
     xcu_stream_wait_event(stream, xg_world_event(w, 1));
@@ -323,7 +354,9 @@ static void pipe_plan(struct gs_data *g)
 {
   if (g->pipe_chunks || !g->nwin) return;
   const size_t n = g->n;
-  unsigned C = (unsigned)(((size_t)n * 8 + (24u << 20) - 1) / (24u << 20));
+  size_t chunk = 24u << 20;                       /* bytes of a double field per chunk */
+  { const char *v = getenv("EXAGS_PIPE_CHUNK_BYTES"); if (v && atol(v) >= 256) chunk = (size_t)atol(v); }
+  unsigned C = (unsigned)(((size_t)n * 8 + chunk - 1) / chunk);
   if (C < 2) return;
   if (C > 128) C = 128;
   const size_t per = (n + C - 1) / C;
@@ -343,13 +376,15 @@ static void pipe_plan(struct gs_data *g)
     while (k < C - 1 && g->pipe_run[k] < s0) ++k;
     g->pipe_out_wave[j] = k;
   }
+  g->pipe_bnd = xnew0(unsigned char, C);
+  for (size_t k = 0; k < g->h_nbidx; ++k) g->pipe_bnd[g->h_bidx[k] / per] = 1;
   g->pipe_ev = xnew(void *, 2 * (size_t)C);
   for (unsigned k = 0; k < 2 * C; ++k) g->pipe_ev[k] = xcu_event_create();
   g->pipe_chunks = C;
 }
 
 static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                                  int xd, int xop)
+                                  int xd, int xop, int transpose)
 {
   struct xg_world *w = g->w;
   const unsigned C = g->pipe_chunks;
@@ -359,12 +394,18 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
   const size_t each = n * esz * tuple;
   char *stage = (char *)xg_world_scratch(w, 2, each * parts);
   void *s_in = xg_world_stream(w, 2), *s_run = xg_world_stream(w, 0), *s_out = xg_world_stream(w, 3);
+  void *scomm = xg_world_stream(w, 1);
   struct xcu_field f; memset(&f, 0, sizeof f);
   f.vn = vn; f.tuple = vn; f.k0 = 0;
-  if (mode == XM_MANY) { if (vn > XG_MAXV) xfail("gs: internal: pipelined path with %u arrays", vn); for (unsigned k = 0; k < vn; ++k) f.p[k] = stage + each * k; }
-  else f.p[0] = stage;
+  void *dptr[XG_MAXV];
+  if (mode == XM_MANY) { if (vn > XG_MAXV) xfail("gs: internal: pipelined path with %u arrays", vn); for (unsigned k = 0; k < vn; ++k) dptr[k] = f.p[k] = stage + each * k; }
+  else dptr[0] = f.p[0] = stage;
+  /* np > 1: the boundary groups run once the whole field is up (their members
+     sit in the first and last layers of a slab); the chunks they touch go
+     back after the unpack, every other chunk as soon as its windows are done */
+  struct bnd_ctx bc;
+  bnd_prepare(g, &bc, vn, xd, transpose);
   u32 done = 0;
-  unsigned next_out = 0;
   for (unsigned k = 0; k < C; ++k) {
     size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
     for (unsigned p = 0; p < parts; ++p)
@@ -379,16 +420,34 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
       done = g->pipe_run[k];
     }
     xcu_event_record(g->pipe_ev[C + k], s_run);
-    while (next_out < C && g->pipe_out_wave[next_out] <= k) {
-      size_t olo = (size_t)next_out * per, ohi = olo + per < n ? olo + per : n;
-      xcu_stream_wait_event(s_out, g->pipe_ev[C + g->pipe_out_wave[next_out]]);
+    if (k == C - 1 && bc.active) {
+      xcu_stream_wait_event(scomm, g->pipe_ev[k]);
+      bnd_pack(g, &bc, dptr, mode, vn, xd, xop, transpose, scomm);
+      bnd_unpack(g, &bc, dptr, mode, vn, xd, xop, transpose, scomm);
+      xcu_event_record(xg_world_event(w, 1), scomm);
+    }
+    for (unsigned j = 0; j < C; ++j) {
+      if (g->pipe_out_wave[j] != k || (bc.active && g->pipe_bnd[j])) continue;
+      size_t olo = (size_t)j * per, ohi = olo + per < n ? olo + per : n;
+      xcu_stream_wait_event(s_out, g->pipe_ev[C + k]);
       for (unsigned p = 0; p < parts; ++p)
         xcu_d2h((char *)ptrs[p] + olo * esz * tuple, stage + each * p + olo * esz * tuple, (ohi - olo) * esz * tuple, s_out);
-      ++next_out;
+    }
+  }
+  if (bc.active) {
+    xcu_stream_wait_event(s_out, xg_world_event(w, 1));
+    xcu_stream_wait_event(s_out, g->pipe_ev[2 * C - 1]);
+    for (unsigned j = 0; j < C; ++j) {
+      if (!g->pipe_bnd[j]) continue;
+      size_t olo = (size_t)j * per, ohi = olo + per < n ? olo + per : n;
+      for (unsigned p = 0; p < parts; ++p)
+        xcu_d2h((char *)ptrs[p] + olo * esz * tuple, stage + each * p + olo * esz * tuple, (ohi - olo) * esz * tuple, s_out);
     }
   }
   xcu_stream_sync(s_out);
   xcu_stream_sync(s_run);
+  if (bc.active) xcu_stream_sync(scomm);
+  push_check(g, "during this call");
 }
 
 static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned transpose,
@@ -430,7 +489,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
     const char *pp = getenv("EXAGS_HOST_PIPELINE");
     if (!(pp && atoi(pp) == 0)) pipe_plan(g);
     if (g->pipe_chunks) {
-      gs_run_host_pipelined(g, ptrs, mode, vn, xd, op);
+      gs_run_host_pipelined(g, ptrs, mode, vn, xd, op, (int)transpose);
       free(ptrs);
       return;
     }
@@ -535,11 +594,12 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     xg_sell_build(&sell, &in);
     g->sell_idx_entries = sell.nidx;
   }
-  if (use_sell && !sell.rest.ng && !nfs && !nb) {
+  if (use_sell && !sell.rest.ng && !nfs) {
     /* keep what the pipelined host path needs to schedule windows by chunk */
     g->nwin = sell.nwin;
     g->win_min = sell.win_min; g->win_max = sell.win_max;
     sell.win_min = sell.win_max = 0;
+    if (nb && bni) { g->h_bidx = xnew(u32, bni); memcpy(g->h_bidx, bgidx, bni * sizeof(u32)); g->h_nbidx = bni; }
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
@@ -752,6 +812,7 @@ void exags_gs_free(struct gs_data *g)
   }
   xg_hmap_free(&g->hall);
   free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);
+  free(g->h_bidx); free(g->pipe_bnd);
   xg_plan_free(&g->plan);
   exags_comm_free(&g->comm);
   free(g);

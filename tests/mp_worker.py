@@ -45,7 +45,7 @@ def main():
     unique = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     method = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rank, np_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    gpu = what == "exec"
+    gpu = what in ("exec", "exech")      # exech: host pointers (staged / pipelined path)
     if not gpu:
         os.environ["EXAGS_HOST_SETUP_ONLY"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=np_)
@@ -86,7 +86,8 @@ def main():
                 if not np.array_equal(got[r], want[r]):
                     print(f"MISMATCH gs_unique rank={r}\n got {got[r][:40]}\n want {want[r][:40]}")
                     ok = False
-    elif what == "exec":
+    elif what in ("exec", "exech"):
+        onhost = what == "exech"
         import itertools
         combos = list(itertools.product(cases.DTYPES.items(), cases.OPS, (0, 1), (0, 1, 2)))
         for (dname, dt), op, t, mode in combos:
@@ -95,14 +96,14 @@ def main():
             dom = X.NP_DOM[np.dtype(dt)]
             if mode == 2:
                 u = [cases.values(ids.size, dt, op, 1000 * rank + k) for k in range(vn)]
-                dev = [torch.from_numpy(x.copy()).cuda() for x in u]
+                dev = [x.copy() if onhost else torch.from_numpy(x.copy()).cuda() for x in u]
                 X.gs_many(dev, vn, dom, opi, t, g)
-                got = [d.cpu().numpy() for d in dev]
+                got = dev if onhost else [d.cpu().numpy() for d in dev]
             else:
                 u = cases.values(ids.size * vn, dt, op, 1000 * rank + 7)
-                dev = torch.from_numpy(u.copy()).cuda()
+                dev = u.copy() if onhost else torch.from_numpy(u.copy()).cuda()
                 (X.gs if mode == 0 else lambda *a: X.gs_vec(a[0], vn, *a[1:]))(dev, dom, opi, t, g)
-                got = dev.cpu().numpy()
+                got = dev if onhost else dev.cpu().numpy()
             ins = gather_arrays(u, np_)
             outs = gather_arrays(got, np_)
             if rank == 0:

@@ -74,3 +74,27 @@ def test_multirank_exec_one_gpu_push(built, np_, case, method, unique):
     codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": "push"})
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case,transport", [(2, "slab", "ipc"), (4, "blocks", "push"), (2, "random", "ipc"),
+                                                 (3, "empty", "push")])
+def test_multirank_host_pointers_one_gpu(built, np_, case, transport):
+    """Host pointers with np > 1: symmetric maps take the chunked H2D / window
+    waves / D2H pipeline with the boundary exchange after the last chunk (tiny
+    chunks here so that small meshes are cut into many); flagged maps take the
+    stage-run-copy path."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, [case, "exech", 0, 1], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": transport,
+                                       "EXAGS_PIPE_CHUNK_BYTES": "512"})
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
+def test_multirank_host_pointers(built, np_, case):
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "exech", 0, 1], timeout=600,
+                            extra_env={"EXAGS_PIPE_CHUNK_BYTES": "512"})
+    assert all(c == 0 for c in codes), "\n".join(outs)

@@ -10,7 +10,7 @@ for spec in sys.argv[1:]:
     env = dict(os.environ)
     for kv in spec.split(","):
         k, v = kv.split("=")
-        env[{"LAYOUT": "EXAGS_LAYOUT", "VARIANT": "EXAGS_SELL_VARIANT", "SIGMA": "EXAGS_SELL_SIGMA"}[k]] = v
+        env[{"LAYOUT": "EXAGS_LAYOUT", "VARIANT": "EXAGS_SELL_VARIANT", "SIGMA": "EXAGS_SELL_SIGMA", "CTAS": "EXAGS_SELL_CTAS"}[k]] = v
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--no-cpu"],
                        env=env, capture_output=True, text=True)
     try:
