@@ -240,7 +240,15 @@ struct xcu_push {
   u32  nsig;                       /* 0: do not signal from this launch             */
   u32  epoch;
   u32 *counter;                    /* CTA completion counter in my mailbox          */
+  const u32 *start;                /* [nnb+1] first send slot of each neighbour (slot-ordered pack) */
+  u32  nnb;
 };
+/* slot-ordered pack (symmetric maps): slot s of the send numbering carries
+   u[sprim[s]], which already holds its group's local total; with pp != NULL
+   the value goes straight into the neighbour's mailbox (consecutive slots of a
+   neighbour are consecutive there, so the NVLink stores coalesce)            */
+void xcu_pack_slots(void *stream, const u32 *sprim, u32 nslots, const struct xcu_field *f,
+                    int mode, int xdom, void *sendbuf, unsigned bufvn, const struct xcu_push *pp);
 void xcu_bnd_pack_push(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
                        int mode, int xdom, int xop, int transpose, unsigned bufvn,
                        const struct xcu_push *pp);

@@ -365,6 +365,43 @@ k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
   }
 }
 
+// Slot-ordered pack for symmetric maps: the boundary groups have been reduced
+// (and scattered) by the sliced-ELL kernel, so u[primary] is the group total
+// and slot s only has to carry u[sprim[s]] -- scatter_to_buf of
+// src/gs.upc:490 read the other way round.  Consecutive threads fill
+// consecutive slots, so the stores into a neighbour's mailbox are contiguous.
+template <typename T, int MODE, bool PUSH>
+__global__ void __launch_bounds__(256)
+k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__restrict__ sendbuf,
+             unsigned bufvn, xcu_push pp)
+{
+  for (u32 s = blockIdx.x * 256u + threadIdx.x; s < nslots; s += gridDim.x * 256u) {
+    const u32 prim = __ldg(sprim + s);
+    T *dst = sendbuf;
+    u32 slot = s;
+    if (PUSH) {
+      u32 lo = 0, hi = pp.nnb;                    // neighbour whose slot range holds s
+      while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (__ldg(pp.start + mid) <= s) lo = mid; else hi = mid; }
+      dst = reinterpret_cast<T *>(__ldg(pp.base + lo));
+      slot = s + __ldg(pp.delta + lo);
+    }
+    for (unsigned k = 0; k < f.vn; ++k)
+      dst[(size_t)slot * bufvn + f.k0 + k] = *f.at(prim, k);
+  }
+  if (PUSH && pp.nsig) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(pp.counter, 1u);
+      if (done == gridDim.x - 1u) {
+        *pp.counter = 0u;
+        __threadfence_system();
+        push_signal_all(pp);
+      }
+    }
+  }
+}
+
 // signal without data (a rank whose boundary groups send nothing this call)
 __global__ void k_push_signal(xcu_push pp)
 {
@@ -630,6 +667,36 @@ void xcu_bnd_pack_push(void *stream, const xcu_bnd *b, const xcu_field *f, int m
       *b, make_fld<T, MODE>(f), transpose, (T *)0, bufvn, 0, *pp)
   FOR_ALL(X)
 #undef X
+  LAUNCHED();
+}
+
+void xcu_pack_slots(void *stream, const u32 *sprim, u32 nslots, const xcu_field *f, int mode,
+                    int xdom, void *sendbuf, unsigned bufvn, const xcu_push *pp)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!nslots) { if (pp && pp->nsig) xcu_push_signal(stream, pp); return; }
+  xcu_push none; memset(&none, 0, sizeof none);
+  const unsigned nb = bnd_blocks(nslots);
+  /* a copy: 8- and 4-byte elements are enough */
+#define Y(T, MODE)                                                            \
+  do {                                                                        \
+    if (pp) k_pack_slots<T, MODE, true><<<nb, 256, 0, st>>>(sprim, nslots, make_fld<T, MODE>(f), (T *)0, bufvn, *pp); \
+    else k_pack_slots<T, MODE, false><<<nb, 256, 0, st>>>(sprim, nslots, make_fld<T, MODE>(f), (T *)sendbuf, bufvn, none); \
+  } while (0)
+#define YM(T)                                                                 \
+  switch (mode) {                                                             \
+    case XM_PLAIN: Y(T, XM_PLAIN); break;                                     \
+    case XM_VEC:   Y(T, XM_VEC); break;                                       \
+    case XM_MANY:  Y(T, XM_MANY); break;                                      \
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad mode %d", mode);      \
+  }
+  switch (xdom) {
+    case XD_F64: case XD_I64: YM(long long); break;
+    case XD_F32: case XD_I32: YM(int); break;
+    default: exags_fail(1, __FILE__, __LINE__, "gs: bad domain %d", xdom);
+  }
+#undef YM
+#undef Y
   LAUNCHED();
 }
 

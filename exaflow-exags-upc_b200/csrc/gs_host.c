@@ -50,12 +50,18 @@ struct gs_data {
   void **pipe_ev;                     /* [2*chunks] events */
   u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
   struct xcu_bnd d_bnd;       /* boundary primaries */
-  void *d_bnd_mem[12];
+  void *d_bnd_mem[20];
   /* push transport (pairwise over peer stores): this handle's mailbox and the
      device tables that say where each neighbour's data area is */
   struct xg_mbox mbox;
   const unsigned char *d_snb[2];
   u32 push_nnbmax;
+  /* symmetric maps: boundary groups in sliced-ELL form too, and the local
+     primary behind every send slot, in slot order */
+  int bnd_fast;
+  struct xcu_sell d_bsell;
+  struct dev_csr d_brest;
+  const u32 *d_sprim[2];
   size_t handle_bytes;
 };
 
@@ -160,7 +166,8 @@ static void exchange_ipc_allreduce(struct gs_data *g, void *acc, size_t count, i
      u64 base[parity][d][nnbmax]   neighbour k's data area for that parity
      u64 sig[nsym]                 my flag inside each neighbour's mailbox
      u32 delta[d][nnbmax]          neighbour's slot number - mine
-     u32 wait[nsym]                neighbour ranks (= flag numbers in my mailbox) */
+     u32 wait[nsym]                neighbour ranks (= flag numbers in my mailbox)
+     u32 start[d][nnbmax+1]        first send slot of each neighbour              */
 static void push_prepare(struct gs_data *g, size_t data_bytes)
 {
   struct xg_world *w = g->w;
@@ -168,7 +175,7 @@ static void push_prepare(struct gs_data *g, size_t data_bytes)
   struct xg_mbox *mb = &g->mbox;
   if (!xg_mbox_ensure(w, mb, pl->sym_rank, pl->nsym, data_bytes) && mb->d_tab) return;
   const u32 nm = pl->nnb[0] > pl->nnb[1] ? pl->nnb[0] : pl->nnb[1], M = nm ? nm : 1, ns = pl->nsym;
-  const size_t n64 = 4 * (size_t)M + ns, n32 = 2 * (size_t)M + ns;
+  const size_t n64 = 4 * (size_t)M + ns, n32 = 2 * (size_t)M + ns + 2 * ((size_t)M + 1);
   u64 *t64 = xnew0(u64, n64 + (n32 + 1) / 2 + 1);
   u32 *t32 = (u32 *)(t64 + n64);
   const int me = xg_world_rank(w);
@@ -183,6 +190,10 @@ static void push_prepare(struct gs_data *g, size_t data_bytes)
     for (u32 k = 0; k < pl->nnb[d]; ++k)
       t32[(size_t)d * M + k] = pl->nb_peer_start[d][k] - pl->nb_start[d][k];
   for (u32 i = 0; i < ns; ++i) t32[2 * (size_t)M + i] = pl->sym_rank[i];
+  for (int d = 0; d < 2; ++d) {
+    u32 *st = t32 + 2 * (size_t)M + ns + (size_t)d * (M + 1);
+    for (u32 k = 0; k <= M; ++k) st[k] = k < pl->nnb[d] ? pl->nb_start[d][k] : pl->total[d];
+  }
   if (mb->d_tab) { xcu_device_sync(); xcu_free(mb->d_tab); }
   mb->d_tab = upload(t64, (n64 + (n32 + 1) / 2 + 1) * sizeof(u64));
   xcu_device_sync();
@@ -261,6 +272,8 @@ static void bnd_prepare(struct gs_data *g, struct bnd_ctx *c, unsigned vn, int x
     c->pp.nsig = pl->nsym; c->pp.epoch = epoch;
     c->pp.counter = (u32 *)((char *)mb->mine + 512);
     c->push_wait = t32 + 2 * (size_t)M;
+    c->pp.start = t32 + 2 * (size_t)M + pl->nsym + (size_t)sd * (M + 1);
+    c->pp.nnb = pl->nnb[sd];
     c->recvbuf = (char *)mb->mine + XG_MBOX_HDR + (size_t)par * mb->data_bytes;
   } else if (xg_world_ipc(w)) {
     c->sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
@@ -280,6 +293,23 @@ static void bnd_pack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, in
 {
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   if (c->allred) xcu_fill_identity(scomm, c->sendbuf, (size_t)g->plan.total_shared * vn, xd, xop);
+  if (g->bnd_fast && !c->allred) {
+    /* symmetric map: reduce+scatter the boundary groups with the same sliced
+       kernel as the interior, then fill the send slots in slot order */
+    const int sd = 1 ^ transpose;
+    for (unsigned k0 = 0; k0 < vn; k0 += step) {
+      struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
+      if (g->d_bsell.nblock) xcu_fused_sell(scomm, &g->d_bsell, &f, mode, xd, xop);
+      xcu_fused(scomm, &g->d_brest.c, &f, mode, xd, xop, transpose);
+    }
+    for (unsigned k0 = 0; k0 < vn; k0 += step) {
+      struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
+      struct xcu_push p1 = c->pp;
+      if (k0 + step < vn) p1.nsig = 0;
+      xcu_pack_slots(scomm, g->d_sprim[sd], g->plan.total[sd], &f, mode, xd, c->sendbuf, vn, c->push ? &p1 : 0);
+    }
+    return;
+  }
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
     if (c->push) {
@@ -626,6 +656,39 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
       UP(d->ord, pl->ord, nb);
       UP(d->pflag, pl->pflag, nb);
       for (int dd = 0; dd < 2; ++dd) UP(g->d_snb[dd], pl->snb[dd], pl->total[dd] ? pl->total[dd] : 1);
+      const char *bf = getenv("EXAGS_BND_FAST");
+      if (!any_flag && !(bf && atoi(bf) == 0)) {
+        /* boundary groups with >= 2 local members, sliced like the interior */
+        struct xg_hmap bh; memset(&bh, 0, sizeof bh);
+        for (u32 b = 0; b < nb; ++b) if (bgoff[b + 1] - bgoff[b] >= 2) { ++bh.ng; bh.ni += bgoff[b + 1] - bgoff[b]; }
+        bh.off = xnew(u32, (size_t)bh.ng + 1); bh.idx = xnew(u32, bh.ni ? bh.ni : 1);
+        { u32 og = 0, oi = 0;
+          for (u32 b = 0; b < nb; ++b) {
+            u32 sz = bgoff[b + 1] - bgoff[b];
+            if (sz < 2) continue;
+            bh.off[og++] = oi; memcpy(bh.idx + oi, bgidx + bgoff[b], (size_t)sz * sizeof(u32)); oi += sz;
+          }
+          bh.off[bh.ng] = oi; }
+        struct xg_sell bs; memset(&bs, 0, sizeof bs);
+        if (bh.ng) {
+          xg_sell_build(&bs, &bh);
+          upload_csr(&g->d_brest, &bs.rest);
+          g->d_bsell.nblock = bs.nblock;
+          if (bs.nblock) {
+            UP(g->d_bsell.mask, bs.mask, (size_t)bs.nblock * 32 + 1);
+            UP(g->d_bsell.idx, bs.idx, bs.nidx ? bs.nidx : 1);
+          }
+        }
+        xg_sell_free(&bs); xg_hmap_free(&bh);
+        for (int dd = 0; dd < 2; ++dd) {
+          u32 *sp = xnew(u32, pl->total[dd] ? pl->total[dd] : 1);
+          for (u32 b = 0; b < nb; ++b)
+            for (u32 q = pl->soff[dd][b]; q < pl->soff[dd][b + 1]; ++q) sp[pl->slot[dd][q]] = pl->bprim[b];
+          UP(g->d_sprim[dd], sp, pl->total[dd] ? pl->total[dd] : 1);
+          free(sp);
+        }
+        g->bnd_fast = 1;
+      }
 #undef UP
     }
     xcu_device_sync();
@@ -807,7 +870,8 @@ void exags_gs_free(struct gs_data *g)
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
     xcu_free(g->d_fs);
     for (int m = 0; m < 2; ++m) xcu_free(g->d_sell_mem[m]);
-    for (int m = 0; m < 12; ++m) xcu_free(g->d_bnd_mem[m]);
+    for (int m = 0; m < 20; ++m) xcu_free(g->d_bnd_mem[m]);
+    xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);
   }
   xg_hmap_free(&g->hall);

@@ -58,6 +58,21 @@ g = X.gs_setup(ids, method=X.gs_pairwise)
 t_setup = time.perf_counter() - t1
 info = g.info()
 dof = (elems.astype(np.uint64)[:, None] * np.uint64(m3) + np.arange(m3, dtype=np.uint64)[None, :]).reshape(-1)
+# one partition-independent 53-bit hash per DOF (of its global DOF number); every field derives from it on the GPU
+with np.errstate(over="ignore"):
+    hbits = semmesh._splitmix64((dof * np.uint64(0x9E3779B97F4A7C15)) ^ np.uint64(semmesh.SEED)) >> np.uint64(11)
+del dof
+hdev = torch.from_numpy(hbits.astype(np.int64)).cuda()
+del hbits
+
+
+def make_field(tdt, opname):
+    """FP: uniform [0.5,1.5); int add/min/max: [-1000,1000]; int mul: {1,2}"""
+    if tdt.is_floating_point:
+        return (0.5 + hdev.to(torch.float64) * (1.0 / (1 << 53))).to(tdt)
+    if opname == "mul":
+        return (1 + (hdev & 1)).to(tdt)
+    return (hdev % 2001 - 1000).to(tdt)
 ids_dev = torch.from_numpy(ids).cuda() - 1           # dense slot of each local DOF
 nglob = (Ex * N + 1) * (Ey * N + 1) * (Ez * N + 1)
 del ids
@@ -97,9 +112,7 @@ for dom in (X.gs_double, X.gs_float, X.gs_int, X.gs_long):
     tdt, ndt = DT[dom]
     for op in (X.gs_add, X.gs_mul, X.gs_min, X.gs_max):
         opname = OPS[op][0]
-        host = semmesh.field_values(dof, ndt, opname)
-        u0 = torch.from_numpy(host).cuda()
-        del host
+        u0 = make_field(tdt, opname)
         u = u0.clone()
         X.gs_async(u, X.mode_plain, 1, dom, op, 0, g, stream)
         torch.cuda.synchronize()
