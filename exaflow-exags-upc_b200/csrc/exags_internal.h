@@ -185,6 +185,8 @@ void  *xcu_stream_create(int high_priority);
 void   xcu_stream_destroy(void *s);
 void   xcu_stream_sync(void *s);
 void  *xcu_event_create(void);
+void  *xcu_event_create_timed(void);
+float  xcu_event_ms(void *a, void *b);
 void   xcu_event_record(void *ev, void *stream);
 void   xcu_stream_wait_event(void *stream, void *ev);
 void   xcu_device_sync(void);
@@ -220,6 +222,8 @@ struct xcu_sell {
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                     int mode, int xdom, int xop);
+void xcu_gather_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
+                     int mode, int xdom, int xop);
 
 /* boundary description on the device (np>1) */
 struct xcu_bnd {

@@ -194,7 +194,10 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 // (BASELINE config 3) and the index block is read once for all of them.
 // one block of one lane: 8 predicated loads per component, segmented scan, 8
 // predicated stores
-template <typename T, int OP, int MODE, int KU>
+// GONLY: gather only -- the group total is written to the group's first slot
+// (the primary) and the other members are left for the unpack kernel, which
+// has to write them anyway once the neighbours' contributions are in.
+template <typename T, int OP, int MODE, int KU, bool GONLY = false>
 __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
                                           const unsigned start)
 {
@@ -223,7 +226,8 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
     for (int kk = 0; kk < KU; ++kk)
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) *f.at(id[j], k0 + kk) = x[kk][j];
+        for (int j = 0; j < 8; ++j)
+          if (id[j] != XG_NONE && (!GONLY || ((start >> j) & 1u))) *f.at(id[j], k0 + kk) = x[kk][j];
       }
   }
 }
@@ -237,7 +241,7 @@ __device__ __forceinline__ void ld_stream8(const u32 *p, uint4 &a, uint4 &b)
                : "l"(p));
 }
 
-template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM = false>
+template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM = false, bool GONLY = false>
 __global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
 k_fused_sell(xcu_sell m, Fld<T, MODE> f)
 {
@@ -248,7 +252,7 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f)
   if (STREAM) ld_stream8(reinterpret_cast<const u32 *>(p), a, b);
   else { a = __ldg(p); b = __ldg(p + 1); }
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
-  sell_lane<T, OP, MODE, KU>(f, a, b, start);
+  sell_lane<T, OP, MODE, KU, GONLY>(f, a, b, start);
 }
 
 // Persistent form: a fixed grid (a multiple of the SM count) walks the windows
@@ -631,6 +635,35 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   LAUNCHED();
 }
 
+/* gather-only form for the boundary groups of symmetric maps */
+void xcu_gather_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mode, int xdom, int xop)
+{
+  if (!m->nblock) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = m->nblock / XG_SELL_WB;
+  const unsigned nthr = 32 * XG_SELL_WB;
+  if (mode == XM_PLAIN || f->vn == 1) {
+    xcu_field f1 = *f;
+    f1.vn = 1; f1.tuple = 1;
+    mode = XM_PLAIN;
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_PLAIN, 1, 6, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
+    FOR_DOM(XM_PLAIN, X)
+#undef X
+  } else if (mode == XM_VEC) {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4), false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f))
+    FOR_DOM(XM_VEC, X)
+#undef X
+  } else {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4), false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f))
+    FOR_DOM(XM_MANY, X)
+#undef X
+  }
+  LAUNCHED();
+}
+
 void xcu_init_list(void *stream, const u32 *list, u32 n, const xcu_field *f, int mode, int xdom,
                    int xop)
 {
@@ -842,6 +875,18 @@ void *xcu_event_create(void)
   cudaEvent_t e;
   CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return (void *)e;
+}
+void *xcu_event_create_timed(void)
+{
+  cudaEvent_t e;
+  CU(cudaEventCreate(&e));
+  return (void *)e;
+}
+float xcu_event_ms(void *a, void *b)
+{
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return ms;
 }
 void xcu_event_record(void *ev, void *st) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
 void xcu_stream_wait_event(void *st, void *ev) { CU(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0)); }

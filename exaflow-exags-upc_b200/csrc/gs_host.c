@@ -294,12 +294,13 @@ static void bnd_pack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, in
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   if (c->allred) xcu_fill_identity(scomm, c->sendbuf, (size_t)g->plan.total_shared * vn, xd, xop);
   if (g->bnd_fast && !c->allred) {
-    /* symmetric map: reduce+scatter the boundary groups with the same sliced
-       kernel as the interior, then fill the send slots in slot order */
+    /* symmetric map: reduce the boundary groups into their primaries with the
+       sliced kernel (gather-only form; the unpack writes the members), then
+       fill the send slots in slot order */
     const int sd = 1 ^ transpose;
     for (unsigned k0 = 0; k0 < vn; k0 += step) {
       struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
-      if (g->d_bsell.nblock) xcu_fused_sell(scomm, &g->d_bsell, &f, mode, xd, xop);
+      if (g->d_bsell.nblock) xcu_gather_sell(scomm, &g->d_bsell, &f, mode, xd, xop);
       xcu_fused(scomm, &g->d_brest.c, &f, mode, xd, xop, transpose);
     }
     for (unsigned k0 = 0; k0 < vn; k0 += step) {
@@ -341,6 +342,61 @@ static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, 
   }
 }
 
+/* EXAGS_TRACE=1: run the stages of every call one after the other on the
+   caller's stream with timing events around them and print the per-stage
+   means at gs_free -- the cost of each stage alone, without the overlap.    */
+static int g_trace = -1;
+static double g_trace_ms[4]; static unsigned long g_trace_calls;
+static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
+                             int xd, int xop, int transpose, void *stream);
+
+static void gs_enqueue_traced(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
+                              int xd, int xop, int transpose, void *stream)
+{
+  static void *ev[5];
+  if (!ev[0]) for (int i = 0; i < 5; ++i) ev[i] = xcu_event_create_timed();
+  struct bnd_ctx bc;
+  bnd_prepare(g, &bc, vn, xd, transpose);
+  xcu_event_record(ev[0], stream);
+  if (bc.active) bnd_pack(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream);
+  xcu_event_record(ev[1], stream);
+  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream);
+  xcu_event_record(ev[2], stream);
+  if (bc.active) {
+    /* exchange alone: the wait (or NCCL), then the unpack */
+    struct bnd_ctx only = bc;
+    (void)only;
+    bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream);
+  }
+  xcu_event_record(ev[3], stream);
+  xcu_stream_sync(stream);
+  for (int i = 0; i < 3; ++i) g_trace_ms[i] += xcu_event_ms(ev[i], ev[i + 1]);
+  ++g_trace_calls;
+}
+
+static void trace_report(struct gs_data *g)
+{
+  if (g_trace <= 0 || !g_trace_calls) return;
+  printf("[exags trace rank %d] %lu calls: boundary reduce+pack %.4f ms, interior %.4f ms, wait+unpack %.4f ms "
+         "(stages serialised; boundary groups %u, send slots %u, interior sliced blocks %u)\n",
+         xg_world_rank(g->w), g_trace_calls, g_trace_ms[0] / g_trace_calls, g_trace_ms[1] / g_trace_calls,
+         g_trace_ms[2] / g_trace_calls, g->plan.nb, g->plan.total[1], g->d_sell.nblock);
+  fflush(stdout);
+  g_trace_calls = 0; g_trace_ms[0] = g_trace_ms[1] = g_trace_ms[2] = 0;
+}
+
+static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
+                             int xd, int xop, int transpose, void *stream)
+{
+  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
+  for (unsigned k0 = 0; k0 < vn; k0 += step) {
+    struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
+    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop);
+    xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
+    if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
+  }
+}
+
 /* Enqueue one gs on device-resident data.  ptrs: vn device pointers for
    mode many, else ptrs[0].  Work is ordered on `stream`.                   */
 static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
@@ -349,6 +405,8 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
   struct xg_world *w = g->w;
   struct bnd_ctx bc;
   void *scomm = xg_world_stream(w, 1);
+  if (g_trace < 0) { const char *v = getenv("EXAGS_TRACE"); g_trace = v ? atoi(v) : 0; }
+  if (g_trace > 0) { gs_enqueue_traced(g, ptrs, mode, vn, xd, xop, transpose, stream); return; }
   bnd_prepare(g, &bc, vn, xd, transpose);
   if (bc.active) {
     /* fork: boundary stream starts after whatever precedes us on `stream` */
@@ -357,13 +415,7 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
     bnd_pack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
   }
   /* interior: fused gather-scatter on the caller's stream */
-  const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
-  for (unsigned k0 = 0; k0 < vn; k0 += step) {
-    struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
-    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop);
-    xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
-    if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
-  }
+  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream);
   if (bc.active) {
     bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
     /* join */
@@ -865,6 +917,7 @@ struct gs_data *exags_gs_setup(const int *id, exags_uint n, const comm_ptr comm,
 void exags_gs_free(struct gs_data *g)
 {
   if (!g) return;
+  trace_report(g);
   if (g->on_device) {
     xcu_device_sync();
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
