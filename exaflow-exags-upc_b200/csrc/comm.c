@@ -704,3 +704,58 @@ double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n)
   exags_comm_allreduce(cp, gs_double, gs_add, &s, 1, &b);
   return s;
 }
+
+/* ------------------------------------------------------------------ */
+/*  element type tags and Fortran bindings (src/comm.upc:376-407,       */
+/*  804-827, 1031-1148)                                                 */
+/* ------------------------------------------------------------------ */
+enum { XCT_INT = 4, XCT_INT8 = 8, XCT_REAL = 10, XCT_DP = 11 };
+
+void exags_comm_type_int(comm_type *ct)  { if (ct) *ct = XCT_INT; }
+void exags_comm_type_int8(comm_type *ct) { if (ct) *ct = XCT_INT8; }
+void exags_comm_type_real(comm_type *ct) { if (ct) *ct = XCT_REAL; }
+void exags_comm_type_dp(comm_type *ct)   { if (ct) *ct = XCT_DP; }
+void exags_comm_tag_ub(const comm_ptr cp, int *ub) { if (cp && ub) *ub = 0; }
+
+void exags_comm_allreduce_cdom(const comm_ptr cp, comm_type cdom, gs_op_t op, void *v,
+                               exags_uint vn, void *buf)
+{
+  if (!cp || !v || !buf) return;
+  gs_dom dom;
+  switch (cdom) {
+    case XCT_INT:  dom = gs_int; break;
+    case XCT_INT8: dom = gs_long; break;
+    case XCT_REAL: dom = gs_float; break;
+    case XCT_DP:   dom = gs_double; break;
+    default: xfail("comm_allreduce_cdom: cannot identify cdom P=%u.", (unsigned)cdom); return;
+  }
+  exags_comm_allreduce(cp, dom, op, v, vn, buf);
+}
+
+#define FCOMM(name) name##_
+#define FCOMM2(ret, name, args, body)                                         \
+  ret FCOMM(name) args body                                                   \
+  extern __typeof__(FCOMM(name)) fgslib_##name##_ __attribute__((alias(#name "_")));
+
+FCOMM2(void, comm_init, (void), { exags_comm_init(); })
+FCOMM2(void, comm_finalize, (void), { exags_comm_finalize(); })
+FCOMM2(void, comm_world, (comm_ptr *cpp), { exags_comm_world(cpp); })
+FCOMM2(void, comm_free, (comm_ptr *cpp), { exags_comm_free(cpp); })
+FCOMM2(void, comm_np, (const comm_ptr *cpp, int *np), { exags_comm_np(*cpp, np); })
+FCOMM2(void, comm_id, (const comm_ptr *cpp, int *id), { exags_comm_id(*cpp, id); })
+FCOMM2(void, comm_type_int, (comm_type *ct), { exags_comm_type_int(ct); })
+FCOMM2(void, comm_type_int8, (comm_type *ct), { exags_comm_type_int8(ct); })
+FCOMM2(void, comm_type_real, (comm_type *ct), { exags_comm_type_real(ct); })
+FCOMM2(void, comm_type_dp, (comm_type *ct), { exags_comm_type_dp(ct); })
+FCOMM2(void, comm_tag_ub, (const comm_ptr *cpp, int *ub), { exags_comm_tag_ub(*cpp, ub); })
+FCOMM2(void, comm_time, (double *tm), { exags_comm_time(tm); })
+FCOMM2(void, comm_barrier, (const comm_ptr *cpp), { exags_comm_barrier(*cpp); })
+FCOMM2(void, comm_bcast, (const comm_ptr *cpp, void *p, size_t *n, exags_uint *root), { exags_comm_bcast(*cpp, p, *n, *root); })
+FCOMM2(void, comm_allreduce_add, (const comm_ptr *cpp, comm_type *ct, void *v, exags_uint *vn, void *buf),
+       { exags_comm_allreduce_cdom(*cpp, *ct, gs_add, v, *vn, buf); })
+FCOMM2(void, comm_allreduce_min, (const comm_ptr *cpp, comm_type *ct, void *v, exags_uint *vn, void *buf),
+       { exags_comm_allreduce_cdom(*cpp, *ct, gs_min, v, *vn, buf); })
+FCOMM2(void, comm_allreduce_max, (const comm_ptr *cpp, comm_type *ct, void *v, exags_uint *vn, void *buf),
+       { exags_comm_allreduce_cdom(*cpp, *ct, gs_max, v, *vn, buf); })
+FCOMM2(void, comm_allreduce_mul, (const comm_ptr *cpp, comm_type *ct, void *v, exags_uint *vn, void *buf),
+       { exags_comm_allreduce_cdom(*cpp, *ct, gs_mul, v, *vn, buf); })

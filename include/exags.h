@@ -208,6 +208,23 @@ void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
                      const void *v, exags_uint vn, void *buffer);
 double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n);
                                                       /* comm.upc:954 */
+/* Element type tags for the Fortran-facing reductions (the reference hands
+   out upc_type_t values, src/comm.h:72, src/comm.upc:376-400; callers only
+   ever obtain them from these four functions).                             */
+typedef int comm_type;
+void exags_comm_type_int(comm_type *ct);              /* comm.upc:376 */
+void exags_comm_type_int8(comm_type *ct);             /* comm.upc:382 */
+void exags_comm_type_real(comm_type *ct);             /* comm.upc:389 */
+void exags_comm_type_dp(comm_type *ct);               /* comm.upc:396 */
+void exags_comm_tag_ub(const comm_ptr cp, int *ub);   /* comm.upc:403 (MPI only: 0) */
+void exags_comm_allreduce_cdom(const comm_ptr cp, comm_type cdom, gs_op_t op,
+                               void *v, exags_uint vn, void *buf);  /* comm.upc:804 */
+/* Fortran bindings of the communicator (src/comm.upc:1031-1148) are exported
+   as comm_init_, comm_finalize_, comm_world_, comm_free_, comm_np_, comm_id_,
+   comm_type_int_, comm_type_int8_, comm_type_real_, comm_type_dp_,
+   comm_tag_ub_, comm_time_, comm_barrier_, comm_bcast_, comm_allreduce_add_,
+   comm_allreduce_min_, comm_allreduce_max_, comm_allreduce_mul_ (and the same
+   with the fgslib_ prefix for a Nek build).                                */
 
 /* ======================================================================
  *  errors                                       replaces src/fail.h:32-38
@@ -286,6 +303,12 @@ void fgslib_gs_free_(const int *handle);
 # define comm_allreduce exags_comm_allreduce
 # define comm_scan      exags_comm_scan
 # define comm_dot       exags_comm_dot
+# define comm_type_int  exags_comm_type_int
+# define comm_type_int8 exags_comm_type_int8
+# define comm_type_real exags_comm_type_real
+# define comm_type_dp   exags_comm_type_dp
+# define comm_tag_ub    exags_comm_tag_ub
+# define comm_allreduce_cdom exags_comm_allreduce_cdom
 # define glb_comm       exags_glb_comm
 # define fail           exags_fail
 # define die            exags_die

@@ -34,6 +34,41 @@ def test_fortran_and_data_symbols(X):
               "gs_setup_pick_", "gs_op", "gs_op_vec", "gs_op_many", "gs_op_fields",
               "exags_glb_comm", "exags_comm_gbl_id", "exags_comm_gbl_np"):
         assert hasattr(L, n), n
+    # communicator Fortran bindings (src/comm.upc:1031-1148), both flavours
+    for n in ("init", "finalize", "world", "free", "np", "id", "type_int", "type_int8", "type_real",
+              "type_dp", "tag_ub", "time", "barrier", "bcast", "allreduce_add", "allreduce_min",
+              "allreduce_max", "allreduce_mul"):
+        assert hasattr(L, f"comm_{n}_"), n
+        assert hasattr(L, f"fgslib_comm_{n}_"), n
+
+
+def test_fortran_comm_bindings_single_rank(X):
+    """By-reference comm calls on one rank: identity, type tags, and an
+    allreduce that must leave the vector unchanged (src/comm.upc:1062-1148)."""
+    import numpy as np
+    L = ctypes.CDLL(X.LIB_PATH)
+    cp = ctypes.c_void_p()
+    L.comm_init_()
+    L.comm_world_(ctypes.byref(cp))
+    npv, idv, ub = ctypes.c_int(-1), ctypes.c_int(-1), ctypes.c_int(-1)
+    L.comm_np_(ctypes.byref(cp), ctypes.byref(npv))
+    L.comm_id_(ctypes.byref(cp), ctypes.byref(idv))
+    L.comm_tag_ub_(ctypes.byref(cp), ctypes.byref(ub))
+    assert (npv.value, idv.value, ub.value) == (1, 0, 0)
+    tags = []
+    for n in ("int", "int8", "real", "dp"):
+        t = ctypes.c_int(-1)
+        getattr(L, f"comm_type_{n}_")(ctypes.byref(t))
+        tags.append(t.value)
+    assert len(set(tags)) == 4
+    v = np.array([1.5, -2.0, 3.25]); buf = np.zeros(3)
+    vn = ctypes.c_uint(3); dp = ctypes.c_int(tags[3])
+    L.comm_allreduce_add_(ctypes.byref(cp), ctypes.byref(dp), v.ctypes.data_as(ctypes.c_void_p), ctypes.byref(vn),
+                          buf.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(v, [1.5, -2.0, 3.25])
+    L.comm_barrier_(ctypes.byref(cp))
+    L.comm_free_(ctypes.byref(cp))
+    assert not cp.value
 
 
 def test_compat_headers_compile(tmp_path):
