@@ -105,6 +105,9 @@ void xg_hmap_free(struct xg_hmap *m);
 struct xg_sell {
   u32  nblock;        /* multiple of XG_SELL_WB                              */
   unsigned char *mask;/* [nblock*32] start mask of each lane                 */
+  unsigned char *fmask;/* [nblock*32] "slot holds a flagged member" mask, NULL for
+                         symmetric maps (src/gs.upc:329-357: map_local[0] leaves
+                         flagged members out, map_local[1] keeps them)        */
   u32 *idx;           /* [nblock*256]                                        */
   size_t nidx;
   u32  nwin;          /* windows = nblock / XG_SELL_WB                       */
@@ -219,9 +222,10 @@ struct xcu_sell {
   u32 nblock;
   const unsigned char *mask;
   const u32 *idx;
+  const unsigned char *fmask;   /* NULL: no flagged members */
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
-                    int mode, int xdom, int xop);
+                    int mode, int xdom, int xop, int transpose);
 void xcu_gather_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                      int mode, int xdom, int xop);
 

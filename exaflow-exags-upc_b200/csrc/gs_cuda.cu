@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include "exags_internal.h"
 
 // ---------------------------------------------------------------------------
@@ -80,12 +81,30 @@ template <typename T, int MODE>
 struct Fld {
   T *p[XG_MAXV];
   unsigned vn, tuple, k0;
+  // component pointer picked with constant indices only: a run-time index
+  // into the kernel-parameter array would make the compiler copy it to local
+  // memory and fetch a pointer from there for every access
+  __device__ __forceinline__ T *comp(unsigned k) const
+  {
+    switch (k) {
+      case 0: return p[0]; case 1: return p[1]; case 2: return p[2]; case 3: return p[3];
+      case 4: return p[4]; case 5: return p[5]; case 6: return p[6]; default: return p[7];
+    }
+  }
   __device__ __forceinline__ T *at(u32 i, unsigned k) const
   {
     if (MODE == XM_PLAIN) return p[0] + i;
     if (MODE == XM_VEC)   return p[0] + (size_t)i * tuple + k0 + k;
-    return p[k] + i;
+    return comp(k) + i;
   }
+  // base of component k and element stride, for loops that visit many indices
+  __device__ __forceinline__ T *base(unsigned k) const
+  {
+    if (MODE == XM_PLAIN) return p[0];
+    if (MODE == XM_VEC)   return p[0] + k0 + k;
+    return comp(k);
+  }
+  __device__ __forceinline__ size_t stride() const { return MODE == XM_VEC ? (size_t)tuple : (size_t)1; }
 };
 
 template <typename T, int MODE>
@@ -197,25 +216,49 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 // GONLY: gather only -- the group total is written to the group's first slot
 // (the primary) and the other members are left for the unpack kernel, which
 // has to write them anyway once the neighbours' contributions are in.
-template <typename T, int OP, int MODE, int KU, bool GONLY = false>
+// FLG: the map has flagged members (bit j of flg: slot j is one).  As
+// gs_aux does with map_local[0] / map_local[1] (src/gs.upc:1181-1184):
+//   transpose == 0: flagged members do not contribute (a group with none
+//                   left reduces to the identity, which is what gs_init writes
+//                   over a flagged primary) and every member is written;
+//   transpose == 1: every member contributes, flagged members other than
+//                   the primary are not written.
+// ONE: all components fit one pass (vn <= KU), so component numbers are
+// compile-time constants and gs_many's pointer table is read with constant
+// indices.
+template <typename T, int OP, int MODE, int KU, bool GONLY = false, bool FLG = false, bool ONE = false>
 __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
-                                          const unsigned start)
+                                          const unsigned start, const unsigned flg = 0u,
+                                          const int transpose = 0)
 {
   const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-  for (unsigned k0 = 0; k0 < f.vn; k0 += KU) {
+  unsigned in = 0u, out = 0u;                 // slots that contribute / are written
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) in |= 1u << j;
+  out = in;
+  if (FLG) { if (transpose) out = in & (~flg | start); else in &= ~flg; }
+  if (GONLY) out &= start;
+  const size_t es = f.stride();
+  for (unsigned k0 = 0; k0 < (ONE ? 1u : f.vn); k0 += KU) {
     T x[KU][8];
+    T *pk[KU];
+#pragma unroll
+    for (int kk = 0; kk < KU; ++kk) pk[kk] = f.base(k0 + kk);
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk)
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) x[kk][j] = *f.at(id[j], k0 + kk);
+        for (int j = 0; j < 8; ++j) {
+          if (FLG) x[kk][j] = ident<T, OP>();
+          if ((in >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
+        }
       }
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk) {
       // forward: running reduction, restarted where a group begins
 #pragma unroll
       for (int j = 1; j < 8; ++j) {
-        const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
+        const T cont = ((in >> j) & 1u) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
         x[kk][j] = ((start >> j) & 1u) ? x[kk][j] : cont;
       }
       // backward: the last slot of a group holds its total; spread it
@@ -227,66 +270,76 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (id[j] != XG_NONE && (!GONLY || ((start >> j) & 1u))) *f.at(id[j], k0 + kk) = x[kk][j];
+          if ((out >> j) & 1u) pk[kk][id[j] * es] = x[kk][j];
       }
   }
 }
 
-// index stream: read once, never reused -- keep it out of L1 and first to go in L2
-// (sm_100 has 256-bit global loads: a lane's 8 slots are one instruction)
-__device__ __forceinline__ void ld_stream8(const u32 *p, uint4 &a, uint4 &b)
-{
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-               : "l"(p));
-}
-
-template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM = false, bool GONLY = false>
+template <typename T, int OP, int MODE, int KU, int MINB, bool GONLY = false, bool FLG = false, bool ONE = false>
 __global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
-k_fused_sell(xcu_sell m, Fld<T, MODE> f)
+k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
 {
   const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
-  uint4 a, b;
-  if (STREAM) ld_stream8(reinterpret_cast<const u32 *>(p), a, b);
-  else { a = __ldg(p); b = __ldg(p + 1); }
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
-  sell_lane<T, OP, MODE, KU, GONLY>(f, a, b, start);
+  const unsigned flg = FLG ? __ldg(m.fmask + (size_t)c * 32u + lane) : 0u;
+  sell_lane<T, OP, MODE, KU, GONLY, FLG, ONE>(f, a, b, start, flg, transpose);
 }
 
-// Persistent form: a fixed grid (a multiple of the SM count) walks the windows
-// with stride gridDim.x and each warp fetches the indices of its next block
-// before it touches the field for the current one, so the index -> field load
-// chain of consecutive blocks overlaps instead of adding up.
-template <typename T, int OP, int MODE, int KU, int MINB, bool STREAM>
+// gs_vec with 3-tuples (a velocity field, BASELINE config 3): a tuple is 3
+// consecutive elements, so its address is aligned to one element only.  Read
+// it as one aligned pair plus one single -- pair first when the index is even,
+// single first when it is odd -- instead of three element loads: two trips
+// through L1 per member instead of three.
+template <typename T> struct Pair;
+template <> struct Pair<double>    { typedef double2 type; };
+template <> struct Pair<float>     { typedef float2 type; };
+template <> struct Pair<int>       { typedef int2 type; };
+template <> struct Pair<long long> { typedef longlong2 type; };
+
+template <typename T, int OP, int MINB>
 __global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
-k_fused_sell_pp(xcu_sell m, Fld<T, MODE> f)
+k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
 {
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const u32 nwin = m.nblock / (u32)XG_SELL_WB;
-  u32 win = blockIdx.x;
-  if (win >= nwin) return;
-  size_t c = (size_t)win * XG_SELL_WB + warp;
-  const u32 *p = m.idx + (c * 32u + lane) * 8u;
-  uint4 a, b;
-  if (STREAM) ld_stream8(p, a, b);
-  else { a = __ldg(reinterpret_cast<const uint4 *>(p)); b = __ldg(reinterpret_cast<const uint4 *>(p) + 1); }
-  unsigned start = __ldg(m.mask + c * 32u + lane);
-  for (;;) {
-    const u32 nxt = win + gridDim.x;
-    uint4 na = a, nb = b; unsigned ns = start;
-    if (nxt < nwin) {
-      c = (size_t)nxt * XG_SELL_WB + warp;
-      p = m.idx + (c * 32u + lane) * 8u;
-      if (STREAM) ld_stream8(p, na, nb);
-      else { na = __ldg(reinterpret_cast<const uint4 *>(p)); nb = __ldg(reinterpret_cast<const uint4 *>(p) + 1); }
-      ns = __ldg(m.mask + c * 32u + lane);
+  typedef typename Pair<T>::type T2;
+  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
+  const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  T x[3][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (id[j] != XG_NONE) {
+      const size_t base = (size_t)id[j] * 3u;
+      const bool odd = id[j] & 1u;
+      const T2 pr = *reinterpret_cast<const T2 *>(u + base + (odd ? 1 : 0));
+      const T sg = u[base + (odd ? 0 : 2)];
+      x[0][j] = odd ? sg : pr.x; x[1][j] = odd ? pr.x : pr.y; x[2][j] = odd ? pr.y : sg;
     }
-    sell_lane<T, OP, MODE, KU>(f, a, b, start);
-    if (nxt >= nwin) break;
-    win = nxt; a = na; b = nb; start = ns;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
+      x[kk][j] = ((start >> j) & 1u) ? x[kk][j] : cont;
+    }
+#pragma unroll
+    for (int j = 6; j >= 0; --j) x[kk][j] = ((start >> (j + 1)) & 1u) ? x[kk][j] : x[kk][j + 1];
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (id[j] != XG_NONE) {
+      const size_t base = (size_t)id[j] * 3u;
+      const bool odd = id[j] & 1u;
+      T2 pr;
+      pr.x = odd ? x[1][j] : x[0][j]; pr.y = odd ? x[2][j] : x[1][j];
+      *reinterpret_cast<T2 *>(u + base + (odd ? 1 : 0)) = pr;
+      u[base + (odd ? 0 : 2)] = odd ? x[0][j] : x[2][j];
+    }
 }
 
 template <typename T, int OP, int MODE>
@@ -582,53 +635,65 @@ void xcu_fused(void *stream, const xcu_csr *m, const xcu_field *f, int mode, int
 }
 
 
-void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mode, int xdom, int xop)
+void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mode, int xdom, int xop,
+                    int transpose)
 {
   if (!m->nblock) return;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = m->nblock / XG_SELL_WB;
   const unsigned nthr = 32 * XG_SELL_WB;
-  static int variant = -1, ctas = 0;
-  if (variant < 0) {
-    const char *v = getenv("EXAGS_SELL_VARIANT"); variant = v ? atoi(v) : 0;
-    v = getenv("EXAGS_SELL_CTAS"); ctas = v ? atoi(v) : 0;
+  if (m->fmask) {
+    /* maps with flagged members: same kernel with the flag mask */
+    if (mode == XM_PLAIN || f->vn == 1) {
+      xcu_field f1 = *f;
+      f1.vn = 1; f1.tuple = 1;
+      mode = XM_PLAIN;
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_PLAIN, 1, 5, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), transpose)
+      FOR_DOM(XM_PLAIN, X)
+#undef X
+    } else if (mode == XM_VEC) {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_VEC, 1, 5, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), transpose)
+      FOR_DOM(XM_VEC, X)
+#undef X
+    } else {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_MANY, 1, 5, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), transpose)
+      FOR_DOM(XM_MANY, X)
+#undef X
+    }
+    LAUNCHED();
+    return;
   }
   if (mode == XM_PLAIN || f->vn == 1) {
     /* one component: a vec/many field with vn == 1 is addressed like a plain one */
     xcu_field f1 = *f;
     f1.vn = 1; f1.tuple = 1;
     mode = XM_PLAIN;
-    if (variant == 0) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
+  k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0)
     FOR_DOM(XM_PLAIN, X)
 #undef X
-    } else {
-      /* tuning variants: persistent grid of 148*ctas CTAs */
-      const unsigned per = ctas > 0 ? (unsigned)ctas : (variant == 3 || variant == 4 ? 4u : 5u);
-      unsigned pg = 148u * per; if (pg > grid) pg = grid;
+  } else if (mode == XM_VEC && f->vn == 3 && f->tuple == 3 && f->k0 == 0 &&
+             ((uintptr_t)f->p[0] % (2 * (xdom == XD_F64 || xdom == XD_I64 ? 8 : 4))) == 0) {
 #define X(T, OP, MODE)                                                        \
-  switch (variant) {                                                          \
-    case 1: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 5, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-    case 2: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 5, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break;  \
-    case 3: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 4, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-    case 4: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 4, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break;  \
-    case 5: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 6, false><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-    case 7: k_fused_sell<T, OP, XM_PLAIN, 1, 6, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-    case 8: k_fused_sell<T, OP, XM_PLAIN, 1, 5, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-    default: k_fused_sell_pp<T, OP, XM_PLAIN, 1, 6, true><<<pg, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1)); break; \
-  }
-    FOR_DOM(XM_PLAIN, X)
+  k_fused_sell_vec3<T, OP, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, (T *)f->p[0])
+    FOR_DOM(XM_VEC, X)
 #undef X
-    }
   } else if (mode == XM_VEC) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f))
+  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), 0)
     FOR_DOM(XM_VEC, X)
+#undef X
+  } else if (f->vn <= 3) {
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 3), false, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), 0)
+    FOR_DOM(XM_MANY, X)
 #undef X
   } else {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f))
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), 0)
     FOR_DOM(XM_MANY, X)
 #undef X
   }
@@ -647,17 +712,17 @@ void xcu_gather_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mo
     f1.vn = 1; f1.tuple = 1;
     mode = XM_PLAIN;
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_PLAIN, 1, 6, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
+  k_fused_sell<T, OP, XM_PLAIN, 1, 6, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0)
     FOR_DOM(XM_PLAIN, X)
 #undef X
   } else if (mode == XM_VEC) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4), false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f))
+  k_fused_sell<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 3 : 4), true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), 0)
     FOR_DOM(XM_VEC, X)
 #undef X
   } else {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4), false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f))
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 3 : 4), true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), 0)
     FOR_DOM(XM_MANY, X)
 #undef X
   }

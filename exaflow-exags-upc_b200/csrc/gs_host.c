@@ -38,7 +38,7 @@ struct gs_data {
   struct dev_csr d_int;       /* interior groups (all groups when np == 1): CSR form,
                                  or only the long-group residue when d_sell is used */
   struct xcu_sell d_sell;     /* interior groups, sliced-ELL form (symmetric maps) */
-  void *d_sell_mem[2];
+  void *d_sell_mem[3];
   size_t sell_idx_entries;
   /* pipelined host-pointer path (np == 1, symmetric map): chunk schedule */
   u32 nwin, *win_min, *win_max;       /* host copies from the sliced layout */
@@ -396,7 +396,7 @@ static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, uns
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
-    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop);
+    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
@@ -502,8 +502,9 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
     if (g->pipe_run[k] > done) {
       struct xcu_sell m = g->d_sell;
       m.idx += (size_t)done * XG_SELL_WB * 256; m.mask += (size_t)done * XG_SELL_WB * 32;
+      if (m.fmask) m.fmask += (size_t)done * XG_SELL_WB * 32;
       m.nblock = (g->pipe_run[k] - done) * XG_SELL_WB;
-      xcu_fused_sell(s_run, &m, &f, mode, xd, xop);
+      xcu_fused_sell(s_run, &m, &f, mode, xd, xop, transpose);
       done = g->pipe_run[k];
     }
     xcu_event_record(g->pipe_ev[C + k], s_run);
@@ -676,7 +677,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   /* symmetric maps take the sliced-ELL layout (EXAGS_LAYOUT=csr keeps CSR) */
   struct xg_sell sell; memset(&sell, 0, sizeof sell);
   const char *lay = getenv("EXAGS_LAYOUT");
-  int use_sell = !in.nunf && in.ng && !(lay && strcmp(lay, "csr") == 0);
+  int use_sell = in.ng && !(lay && strcmp(lay, "csr") == 0);
   if (use_sell) {
     xg_sell_build(&sell, &in);
     g->sell_idx_entries = sell.nidx;
@@ -694,6 +695,10 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     g->d_sell_mem[0] = upload(sell.mask, (size_t)sell.nblock * 32 + 1);
     g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
     g->d_sell.mask = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
+    if (sell.fmask) {
+      g->d_sell_mem[2] = upload(sell.fmask, (size_t)sell.nblock * 32 + 1);
+      g->d_sell.fmask = (const unsigned char *)g->d_sell_mem[2];
+    }
   }
   if (g->on_device) {
     if (!use_sell) upload_csr(&g->d_int, &in);
@@ -927,7 +932,7 @@ void exags_gs_free(struct gs_data *g)
     xcu_device_sync();
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
     xcu_free(g->d_fs);
-    for (int m = 0; m < 2; ++m) xcu_free(g->d_sell_mem[m]);
+    for (int m = 0; m < 3; ++m) xcu_free(g->d_sell_mem[m]);
     for (int m = 0; m < 20; ++m) xcu_free(g->d_bnd_mem[m]);
     xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);

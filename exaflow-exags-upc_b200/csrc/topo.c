@@ -174,7 +174,7 @@ u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *c
 /* ------------------------------------------------------------------ */
 void xg_sell_free(struct xg_sell *s)
 {
-  free(s->mask); free(s->idx); free(s->win_min); free(s->win_max);
+  free(s->mask); free(s->fmask); free(s->idx); free(s->win_min); free(s->win_max);
   xg_hmap_free(&s->rest);
   memset(s, 0, sizeof *s);
 }
@@ -194,12 +194,14 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   s->rest.ng = (u32)nlong; s->rest.ni = (u32)ilong;
   s->rest.off = xnew(u32, nlong + 1);
   s->rest.idx = xnew(u32, ilong ? ilong : 1);
+  if (m->nunf) s->rest.nunf = xnew(u32, nlong ? nlong : 1);
   u32 *sg = xnew(u32, nshort ? nshort : 1);        /* short groups, primary order */
   {
     size_t og = 0, oi = 0, os = 0;
     for (u32 g = 0; g < m->ng; ++g) {
       u32 a = m->off[g], sz = m->off[g + 1] - a;
       if (sz > XG_SELL_WMAX) {
+        if (s->rest.nunf) s->rest.nunf[og] = m->nunf[g];
         s->rest.off[og++] = (u32)oi;
         memcpy(s->rest.idx + oi, m->idx + a, (size_t)sz * sizeof(u32));
         oi += sz;
@@ -241,6 +243,7 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   s->win_min = xnew(u32, nwin ? nwin : 1);
   s->win_max = xnew(u32, nwin ? nwin : 1);
   s->mask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
+  if (m->nunf) s->fmask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
 #ifdef _OPENMP
 #pragma omp parallel num_threads(xg_setup_threads())
@@ -281,6 +284,10 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
           u32 *slot = base + (size_t)pos * 8 + fill[pos];
           for (u32 q = 0; q < sz; ++q) slot[q] = m->idx[a + q];
           mk[pos] |= (unsigned char)(1u << fill[pos]);
+          if (s->fmask) {                            /* members [nunf, sz) are flagged */
+            u32 unf = m->nunf[g];
+            s->fmask[w * XG_SELL_WB * 32 + pos] |= (unsigned char)((((1u << sz) - 1u) & ~((1u << unf) - 1u)) << fill[pos]);
+          }
           fill[pos] = (unsigned char)(fill[pos] + wd);
           /* row-major dealing: move on to the next lane; wrap to start a new
              row of this width */

@@ -346,3 +346,49 @@ def test_pipelined_host_path(X):
     for a, b in zip(hm, dm):
         assert np.array_equal(a, b.cpu().numpy())
     X.gs_free(g)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32, np.int32, np.int64])
+def test_vec3_aligned_and_unaligned(X, O, dt):
+    """gs_vec with 3-tuples takes the pair+single load kernel when the field is
+    aligned to two elements and the generic one when it is not (a view that
+    starts one element into an allocation); both must equal the oracle."""
+    ids = semmesh.box_ids(5, 4, 3, 4)
+    n = ids.size
+    g = X.gs_setup(ids)
+    o = O.Oracle([ids])
+    dom, odom = X.NP_DOM[np.dtype(dt)], O.NP_DOM[np.dtype(dt)]
+    for op in ("add", "max"):
+        opi = cases.OPS.index(op)
+        u = cases.values(3 * n, dt, op, 77)
+        want = u.copy()
+        o.exec([want], O.M_VEC, 3, odom, opi, 0)
+        d = _dev(u)
+        X.gs_vec(d, 3, dom, opi, 0, g)
+        assert np.array_equal(d.cpu().numpy(), want), ("aligned", op)
+        big = torch.zeros(3 * n + 1, dtype=d.dtype, device="cuda")
+        view = big[1:]
+        view.copy_(torch.from_numpy(u))
+        assert view.data_ptr() % (2 * view.element_size()) != 0
+        X.gs_vec(view.data_ptr(), 3, dom, opi, 0, g)
+        assert np.array_equal(view.cpu().numpy(), want), ("unaligned", op)
+    X.gs_free(g)
+
+
+def test_flagged_large_sliced(X, O):
+    """A map with flagged members large enough to fill many sliced-ELL windows
+    (flag mask path of the hot kernel), plain / vec / many, both transposes."""
+    ids = semmesh.box_ids(8, 8, 6, 5)
+    ids = ids.copy()
+    rng = np.random.default_rng(11)
+    flip = rng.random(ids.size) < 0.3
+    ids[flip] = -ids[flip]
+    ids[rng.random(ids.size) < 0.02] = 0
+    g = X.gs_setup(ids)
+    o = O.Oracle([ids])
+    for dt, op, t, mode, vn in ((np.float64, "add", 0, 0, 1), (np.float64, "add", 1, 0, 1),
+                                (np.float32, "mul", 1, 1, 3), (np.int32, "min", 0, 2, 3),
+                                (np.int64, "max", 1, 2, 2), (np.float64, "max", 0, 1, 2)):
+        got, want = _run_both(X, O, g, o, dt, op, t, mode, vn, ids.size, 5)
+        assert np.array_equal(got, want), (dt, op, t, mode)
+    X.gs_free(g)

@@ -79,5 +79,5 @@ ids2[::7] = -ids2[::7]
 g2 = X.gs_setup(ids2)
 i2 = g2.info()
 G, S = i2["groups"], i2["members"]
-run("gs(add,double) flagged (CSR path)", X.mode_plain, 1, X.gs_double, X.gs_add, g2, idx_bytes=4 * S + 8 * G + 4)
+run("gs(add,double) flagged 1-in-7 (sliced + init list)", X.mode_plain, 1, X.gs_double, X.gs_add, g2, idx_bytes=4 * S + 8 * G + 4)
 X.gs_free(g2)
