@@ -6,7 +6,8 @@
 A "step" is one gs(add,double) over one rank-local field of the synthetic
 Nek5000-style mesh: at N=1 the M7 box 64x64x48, order 7
 (100 663 296 DOF); at N>1 the same box per GPU as z-slabs of a 64x64x(48N)
-mesh (weak scaling, pairwise halo exchange over NCCL).
+mesh (weak scaling; pairwise halo exchange by peer stores over NVLink from the
+boundary pack kernel, or NCCL send/recv with EXAGS_EXCHANGE=nccl).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput,
 `e2e` the same call made with pinned HOST buffers through the public gs()
@@ -200,6 +201,7 @@ def run_gpu(args) -> None:
     g = X.gs_setup(ids, method=X.gs_pairwise, verbose=0)
     t_setup = time.perf_counter() - t1
     info = g.info()
+    transport = X.exchange_transport()
     del ids
     dof = semmesh.slab_dof_numbers(EX, EY, EZ, ORDER, rank * EZ)
     host = torch.from_numpy(semmesh.field_values(dof, np.float64)).pin_memory()
@@ -292,9 +294,11 @@ def run_gpu(args) -> None:
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"M7 {EX}x{EY}x{EZ} hex N={ORDER} per GPU "
                                        f"({n} DOF/GPU, G={G}, S={S}), gs(add,double), "
-                                       + ("1 rank" if world == 1 else f"z-slabs of {EX}x{EY}x{EZ * world}, pairwise halo over NCCL"),
+                                       + ("1 rank" if world == 1 else
+                                          f"z-slabs of {EX}x{EY}x{EZ * world}, pairwise halo exchange ({transport})"),
                            "l2": "field (805 MB/GPU) is larger than the 126 MB L2; no flush needed",
-                           "setup_s": t_setup, "method": "pairwise"},
+                           "setup_s": t_setup, "method": "pairwise", "exchange": transport,
+                           "halo_bytes_sent_per_rank_per_step": 8 * info["send_slots"]},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "roofline": roofline, "cpu_baseline": cb}
         print(json.dumps(line), flush=True)

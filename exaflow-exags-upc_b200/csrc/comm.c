@@ -437,6 +437,23 @@ struct xg_world *xg_world_get(void)
       if (p != w->rank && memcmp(all + 16 * p, mine, 16) != 0 && !xcu_peer_ok(w->device, all + 16 * p)) ok = 0;
     xg_host_allgather(w, &ok, 1, oks);
     for (int p = 0; p < w->np; ++p) ok &= oks[p];
+    if (ok) {
+      /* and CUDA IPC must work between the processes (it does not across some
+         container boundaries): every rank maps a probe buffer of the next one */
+      char h[64], *hs = xnew(char, 64 * (size_t)w->np);
+      void *probe = xcu_malloc(256);
+      xcu_ipc_export(h, probe);
+      xg_host_allgather(w, h, 64, hs);
+      void *q = xcu_ipc_try_open(hs + 64 * (size_t)((w->rank + 1) % w->np));
+      ok = q != 0;
+      if (q) xcu_ipc_close(q);
+      xg_host_allgather(w, &ok, 1, oks);
+      ok = 1;
+      for (int p = 0; p < w->np; ++p) ok &= oks[p];
+      xg_host_barrier(w);
+      xcu_free(probe);
+      free(hs);
+    }
     free(oks);
     free(all);
     const char *ex = getenv("EXAGS_EXCHANGE");
@@ -542,6 +559,13 @@ void xg_mbox_free(struct xg_world *w, struct xg_mbox *mb)
   mbox_close(w, mb);
   free(mb->peer); mb->peer = 0;
   if (mb->d_tab) { xcu_free(mb->d_tab); mb->d_tab = 0; }
+}
+
+const char *exags_exchange_transport(void)
+{
+  struct xg_world *w = xg_world_get();
+  if (w->np == 1) return "single";
+  return w->use_push ? "push" : w->use_ipc ? "ipc" : "nccl";
 }
 
 void exags_set_device(int device) { g_device_override = device; }

@@ -199,6 +199,7 @@ unsigned long long xcu_launch_count(void);
 void   xcu_ipc_export(void *handle64, void *devptr);
 void  *xcu_ipc_open(const void *handle64);
 void   xcu_ipc_close(void *p);
+void  *xcu_ipc_try_open(const void *handle64);
 void   xcu_device_uuid(int dev, char out16[16]);
 int    xcu_peer_ok(int dev, const char uuid16[16]);   /* can dev store into the device with that uuid? */
 void  *xcu_host_alloc_mapped(size_t bytes);

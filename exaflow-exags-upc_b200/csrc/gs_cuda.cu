@@ -973,6 +973,15 @@ void *xcu_ipc_open(const void *handle64)
   return p;
 }
 void xcu_ipc_close(void *p) { if (p) CU(cudaIpcCloseMemHandle(p)); }
+/* non-fatal open, for the start-up probe of the push transport */
+void *xcu_ipc_try_open(const void *handle64)
+{
+  cudaIpcMemHandle_t h;
+  void *p = 0;
+  memcpy(&h, handle64, 64);
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return p;
+}
 void xcu_device_uuid(int dev, char out16[16])
 {
   cudaDeviceProp pr;

@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.exags_gs_dump_map.argtypes = [vp, i32, vp, C.c_size_t]
     L.exags_gs_dump_map.restype = C.c_size_t
     L.exags_kernel_launches.restype = C.c_ulonglong
+    L.exags_exchange_transport.restype = C.c_char_p
     L.exags_set_device.argtypes = [i32]
     L.exags_get_device.restype = i32
     L.exags_device_malloc.argtypes = [C.c_size_t]
@@ -225,6 +226,11 @@ def gs_unique(ids: np.ndarray, comm=None) -> None:
         lib().exags_gs_unique(ids.ctypes.data, ids.size, cp)
     else:
         raise TypeError("ids must be int32 or int64")
+
+
+def exchange_transport() -> str:
+    """'single' | 'push' | 'nccl' | 'ipc' (include/exags_cuda.h)."""
+    return lib().exags_exchange_transport().decode()
 
 
 def kernel_launches() -> int:

@@ -27,6 +27,13 @@ void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op,
 void exags_set_device(int device);
 int  exags_get_device(void);
 
+/* How ranks exchange halo values: "single" (one rank), "push" (the pack kernel
+   stores into the neighbours' mailboxes over NVLink / peer access -- default
+   between distinct GPUs), "nccl" (grouped ncclSend/ncclRecv; EXAGS_EXCHANGE=nccl
+   or no peer access), "ipc" (CUDA-IPC pulls with host barriers, for ranks that
+   share a GPU).  EXAGS_EXCHANGE=push|nccl|ipc overrides the choice.          */
+const char *exags_exchange_transport(void);
+
 /* Introspection used by the parity tests and the bench.                    */
 /* Number of library kernels launched since process start.                  */
 unsigned long long exags_kernel_launches(void);
