@@ -122,7 +122,16 @@ def cpu_arm(steps: int, warmup: int, seconds_budget: float = 25.0) -> dict:
         reps = max(3, min(steps, 10))
         data = [[semmesh.field_values(semmesh.slab_dof_numbers(EX, EY, ez_per, ORDER, r * ez_per), np.float64)
                  for r in range(ranks)]]
-        _, times = ref.run(ids, [(0, 1, 0, 0, 0)], data, method=1, reps=reps, arena_bytes=(6 << 30))
+        # the shim's bump arena never frees and comm_alloc_thrd_buf keeps np mailboxes of the whole
+        # receive volume per rank (src/comm.upc:174-179): size it by ranks^2; pages are only
+        # committed when touched (MAP_NORESERVE)
+        arena = 2 * ((1 << 30) + n_total * 100 + ranks * ranks * (8 << 20))
+        try:
+            memtotal = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+            arena = min(arena, memtotal // 2)
+        except (ValueError, OSError):
+            pass
+        _, times = ref.run(ids, [(0, 1, 0, 0, 0)], data, method=1, reps=reps, arena_bytes=arena)
         ms = 1e3 * float(times[0])
         return {"value": n_total / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": ranks, "kind": "reference",
                 "sample": sample + f", reference's own code as forked UPC threads, 2 warm + {reps} timed calls",

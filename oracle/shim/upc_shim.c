@@ -112,10 +112,19 @@ int shim_run(int threads, void (*fn)(int, void *), void *arg)
       _exit(0);
     }
   }
-  for (int r = 0; r < threads; ++r) {
+  /* a thread that dies (arena exhausted, fail()) leaves the others spinning
+     on a barrier: reap in any order and take the rest down with it */
+  for (int left = threads; left > 0; --left) {
     int st = 0;
-    waitpid(pid[r], &st, 0);
-    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1;
+    pid_t p = waitpid(-1, &st, 0);
+    if (p < 0) { bad = 1; break; }
+    int mine = 0;
+    for (int r = 0; r < threads; ++r) if (pid[r] == p) { pid[r] = 0; mine = 1; }
+    if (!mine) { ++left; continue; }
+    if ((!WIFEXITED(st) || WEXITSTATUS(st) != 0) && !bad) {
+      bad = 1;
+      for (int r = 0; r < threads; ++r) if (pid[r] > 0) kill(pid[r], SIGKILL);
+    }
   }
   free(pid);
   return bad;

@@ -45,7 +45,7 @@ def main():
     unique = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     method = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rank, np_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    gpu = what in ("exec", "exech")      # exech: host pointers (staged / pipelined path)
+    gpu = what in ("exec", "exech", "exec2")   # exech: host pointers (staged / pipelined path)
     if not gpu:
         os.environ["EXAGS_HOST_SETUP_ONLY"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=np_)
@@ -124,6 +124,36 @@ def main():
                         print(f"MISMATCH exec case={case} {dname} {op} t={t} mode={mode} rank={r}: "
                               f"{bad.size} of {w.size} differ, first at {bad[:5]}")
                         ok = False
+    elif what == "exec2":
+        # two live handles with different neighbour sets, calls interleaved
+        # (Nek keeps one handle per mesh): each has its own mailbox and epoch
+        ids_b = make_ids("slab" if case != "slab" else "blocks", np_, rank)
+        gb = X.gs_setup(ids_b, method=method)
+        all_b = gather_arrays(ids_b, np_)
+        orc_b = O.Oracle(all_b, method=O.METHOD_PAIRWISE) if rank == 0 else None
+        for it in range(6):
+            for (hid, hh, oo, nn) in ((0, g, orc, ids.size), (1, gb, orc_b, ids_b.size)):
+                if it % 3 == 2 and hid == 0:
+                    continue                      # uneven call counts per handle
+                dt, op = (np.float64, "add") if (it + hid) % 2 == 0 else (np.int32, "max")
+                vn = 1 + (it % 2) * 2
+                u = cases.values(nn * vn, dt, op, 100 * rank + 10 * it + hid)
+                dev = torch.from_numpy(u.copy()).cuda()
+                dom, opi = X.NP_DOM[np.dtype(dt)], cases.OPS.index(op)
+                t = it % 2
+                if vn == 1:
+                    X.gs(dev, dom, opi, t, hh)
+                else:
+                    X.gs_vec(dev, vn, dom, opi, t, hh)
+                ins, outs = gather_arrays(u, np_), gather_arrays(dev.cpu().numpy(), np_)
+                if rank == 0:
+                    want = [a.copy() for a in ins]
+                    oo.exec(want, 0 if vn == 1 else 1, vn, O.NP_DOM[np.dtype(dt)], opi, t)
+                    for r in range(np_):
+                        if not np.array_equal(outs[r], want[r]):
+                            print(f"MISMATCH exec2 it={it} handle={hid} rank={r}")
+                            ok = False
+        X.gs_free(gb)
     flag = torch.tensor([0 if ok else 1])
     dist.broadcast(flag, 0)
     X.gs_free(g)

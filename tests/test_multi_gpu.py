@@ -98,3 +98,22 @@ def test_multirank_host_pointers(built, np_, case):
     codes, outs = run_ranks(np_, [case, "exech", 0, 1], timeout=600,
                             extra_env={"EXAGS_PIPE_CHUNK_BYTES": "512"})
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,transport", [(3, "push"), (4, "push"), (2, "ipc")])
+def test_two_handles_interleaved_one_gpu(built, np_, transport):
+    """Two live handles (different label sets, hence different neighbour sets
+    and slot ranges) called alternately, with uneven call counts: every handle
+    has its own mailbox and epoch, so their exchanges cannot mix."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, ["blocks", "exec2", 0, 1], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": transport})
+    assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+def test_two_handles_interleaved(built):
+    if _ndev() < 4:
+        pytest.skip(f"needs 4 GPUs, have {_ndev()}")
+    codes, outs = run_ranks(4, ["blocks", "exec2", 0, 1], timeout=600)
+    assert all(c == 0 for c in codes), "\n".join(outs)
