@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -237,7 +237,6 @@ def run_gpu(args) -> None:
         ev[k + 1].record()
     barrier()
     launches = X.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     per = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
     if dist is not None:
@@ -258,6 +257,7 @@ def run_gpu(args) -> None:
         X.gs(hbuf.numpy(), X.gs_double, X.gs_add, 0, g)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - w0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     if dist is not None:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -835,6 +835,11 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
   i64 *id_own = 0;
   struct xg_topo topo;
   struct xg_shared sh;
+  const char *prof_env = getenv("EXAGS_SETUP_PROFILE");
+  const int prof = prof_env && atoi(prof_env) && comm->id == 0;
+  double tp[8]; int ntp = 0;
+#define TICK() do { if (prof) exags_comm_time(&tp[ntp++]); } while (0)
+  TICK();
   xg_topo_build(&topo, id, n);
   xg_shared_discover(&sh, &topo, w);
   if (unique) {
@@ -853,17 +858,28 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
     xg_shared_discover(&sh, &topo, w);
   }
 
+  TICK();
   xg_topo_local_map(&topo, 1, &g->hall);
   g->hfp = xg_topo_flagged_primaries(&topo, 0, &g->nfp);
+  TICK();
   g->sectors_f64 = count_sectors(&g->hall, 8);
   g->handle_bytes = sizeof *g;
-
+  TICK();
   xg_plan_build(&g->plan, &sh, &topo);
+  TICK();
   split_groups(g, &topo);
+  TICK();
+  if (prof)
+    printf("gs_setup profile (rank 0, n=%u): label sort+groups(+shared discovery) %.3f s, local map %.3f s, "
+           "sector count %.3f s, exchange plan %.3f s, split + sliced layout + upload %.3f s\n", n,
+           tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
+#undef TICK
   /* the NCCL communicator is created here, collectively, never lazily inside
      a ncclGroupStart/End bracket */
   if (np > 1) xg_plan_exchange_offsets(&g->plan, w);
-  if (np > 1 && g->on_device && !xg_world_ipc(w)) (void)xg_world_nccl(w);
+  if (np > 1 && g->on_device && !xg_world_ipc(w) &&
+      (!xg_world_push(w) || method == gs_all_reduce || method == gs_auto))
+    (void)xg_world_nccl(w);       /* the push transport needs NCCL only for the all-reduce method */
   xg_shared_free(&sh);
   xg_topo_free(&topo);
   free(id_own);

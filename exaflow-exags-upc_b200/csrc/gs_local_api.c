@@ -77,7 +77,7 @@ static void side_open(struct side *s, void *ptr, int mode, unsigned vn, size_t e
   size_t each = s->is_many ? extent * esz : extent * esz * (mode == XM_VEC ? vn : 1);
   unsigned parts = s->is_many ? vn : 1;
   if (!s->host) { for (unsigned k = 0; k < parts; ++k) s->dev[k] = s->user[k]; return; }
-  s->stage = xcu_malloc(each * parts ? each * parts : 1);
+  s->stage = xcu_malloc(each * parts);
   for (unsigned k = 0; k < parts; ++k) {
     s->dev[k] = (char *)s->stage + each * k;
     if (copy_in) xcu_h2d(s->dev[k], s->user[k], each, 0);

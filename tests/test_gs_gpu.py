@@ -392,3 +392,21 @@ def test_flagged_large_sliced(X, O):
         got, want = _run_both(X, O, g, o, dt, op, t, mode, vn, ids.size, 5)
         assert np.array_equal(got, want), (dt, op, t, mode)
     X.gs_free(g)
+
+
+def test_c_caller_links_and_runs(X, tmp_path):
+    """A C program written against the reference's headers and spellings, linked
+    with -lexags and run: the drop-in boundary exercised without Python in between."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(X.LIB_PATH)
+    exe = tmp_path / "caller_run"
+    for flags in ([], ["-DGLOBAL_LONG_LONG"]):
+        r = subprocess.run(["gcc", "-std=gnu99", "-O1", os.path.join(root, "tests", "c", "caller_run.c"),
+                            "-I", os.path.join(root, "include"), "-L", libdir, "-lexags",
+                            f"-Wl,-rpath,{libdir}", "-o", str(exe)] + flags, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "EXAGS_HOST_SETUP_ONLY")}
+        r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0 and "caller_run ok" in r.stdout, r.stdout + r.stderr
