@@ -34,6 +34,7 @@
 #include <unistd.h>
 #include <float.h>
 #include <limits.h>
+#include <stdint.h>
 #include "exags_internal.h"
 
 #define XW_MAXNP   64
@@ -685,6 +686,9 @@ static void host_identity(void *out, size_t n, int xd, int xop)
 #undef FILL
 }
 
+/* v may be a host vector (the reference's contract) or a device vector: small
+   device vectors are folded on the host in rank order like host ones (bit-
+   identical on every rank), large ones go through ncclAllReduce in place.     */
 void exags_comm_allreduce(const comm_ptr cp, gs_dom dom, gs_op_t op, void *v, exags_uint vn, void *buf)
 {
   (void)buf;
@@ -693,10 +697,23 @@ void exags_comm_allreduce(const comm_ptr cp, gs_dom dom, gs_op_t op, void *v, ex
   if (xd < 0) xfail("comm_allreduce: bad domain %d", (int)dom);
   struct xg_world *w = (struct xg_world *)cp->priv;
   size_t bytes = (size_t)vn * xg_dom_bytes(xd);
-  char *all = (char *)xmalloc_(bytes * (size_t)cp->np, __FILE__, __LINE__);
-  xg_host_allgather(w, v, bytes, all);
-  memcpy(v, all, bytes);
-  for (int p = 1; p < cp->np; ++p) host_combine(v, all + (size_t)p * bytes, vn, xd, (int)op);
+  const int on_dev = w->has_cuda && xcu_is_device_ptr(v);
+  if (on_dev && bytes > (1u << 20) && !w->use_ipc && (int)op <= XO_MAX) {
+    void *s = w->stream[1];
+    xcu_device_sync();
+    xg_nccl_allreduce(w, v, vn, xd, (int)op, s);
+    xcu_stream_sync(s);
+    return;
+  }
+  char *all = (char *)xmalloc_(bytes * ((size_t)cp->np + 1), __FILE__, __LINE__);
+  char *mine = all + bytes * (size_t)cp->np;
+  if (on_dev) { xcu_device_sync(); xcu_d2h(mine, v, bytes, 0); xcu_device_sync(); }
+  else memcpy(mine, v, bytes);
+  xg_host_allgather(w, mine, bytes, all);
+  memcpy(mine, all, bytes);
+  for (int p = 1; p < cp->np; ++p) host_combine(mine, all + (size_t)p * bytes, vn, xd, (int)op);
+  if (on_dev) { xcu_h2d(v, mine, bytes, 0); xcu_device_sync(); }
+  else memcpy(v, mine, bytes);
   free(all);
 }
 
@@ -724,7 +741,18 @@ void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
 double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n)
 {
   double s = 0, b;
-  for (exags_uint i = 0; i < n; ++i) s += v[i] * w[i];
+  struct xg_world *wd = cp ? (struct xg_world *)cp->priv : 0;
+  if (wd && wd->has_cuda && n && xcu_is_device_ptr(v)) {
+    /* device vectors: HBM-bound two-pass reduction in a fixed order */
+    if (!xcu_is_device_ptr(w)) xfail("comm_dot: v is a device vector, w is not");
+    if (((uintptr_t)v | (uintptr_t)w) & 15u) xfail("comm_dot: device vectors must be 16-byte aligned");
+    double *scr = (double *)xg_world_scratch(wd, 3, ((size_t)xcu_dot_parts() + 1) * sizeof(double));
+    void *st = wd->stream[0];
+    xcu_dot(st, v, w, n, scr + 1, scr);
+    xcu_d2h(&s, scr, sizeof s, st);
+    xcu_stream_sync(st);
+  } else
+    for (exags_uint i = 0; i < n; ++i) s += v[i] * w[i];
   exags_comm_allreduce(cp, gs_double, gs_add, &s, 1, &b);
   return s;
 }

@@ -279,6 +279,8 @@ void xcu_bnd_pack(void *stream, const struct xcu_bnd *b, const struct xcu_field 
 void xcu_bnd_unpack(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose, const void *recvbuf,
                     unsigned bufvn, int allreduce);
+unsigned xcu_dot_parts(void);
+void xcu_dot(void *stream, const double *v, const double *w, size_t n, double *scratch, double *out);
 void xcu_fill_identity(void *stream, void *out, size_t n, int xdom, int xop);
 void xcu_array_op(void *stream, void *out, const void *in, size_t n, int xdom, int xop);
 /* generic CSR gather / scatter between two (possibly different) fields:

@@ -568,6 +568,41 @@ k_csr_scatter(xcu_csr m, FldR<T> out, FldR<T> in)
   }
 }
 
+// comm_dot on device vectors (src/comm.upc:954-959, src/tensor.c:12-17): the
+// other per-iteration reduction a Nek solver issues next to gs.  Two passes,
+// both in a fixed order (a CTA's threads stride the vector, a tree inside the
+// CTA, then one CTA folds the partials left to right), so the result does not
+// depend on scheduling; it is a different association than the reference's
+// serial loop, hence equal only up to rounding.  HBM-bound: 16 B per element.
+#define DOT_THREADS 256
+__global__ void __launch_bounds__(DOT_THREADS)
+k_dot_partial(const double *__restrict__ v, const double *__restrict__ w, size_t n, double *__restrict__ part)
+{
+  __shared__ double sh[DOT_THREADS];
+  const size_t n2 = n / 2, stride = (size_t)gridDim.x * DOT_THREADS;
+  const double2 *v2 = reinterpret_cast<const double2 *>(v), *w2 = reinterpret_cast<const double2 *>(w);
+  double acc0 = 0, acc1 = 0;
+  for (size_t i = (size_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n2; i += stride) {
+    const double2 a = __ldg(v2 + i), b = __ldg(w2 + i);
+    acc0 = fma(a.x, b.x, acc0); acc1 = fma(a.y, b.y, acc1);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) acc0 = fma(v[n - 1], w[n - 1], acc0);
+  sh[threadIdx.x] = acc0 + acc1;
+  __syncthreads();
+  for (unsigned s = DOT_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
+__global__ void k_dot_final(const double *__restrict__ part, unsigned nparts, double *__restrict__ out)
+{
+  double s = 0;
+  for (unsigned i = 0; i < nparts; ++i) s += part[i];
+  *out = s;
+}
+
 // ---------------------------------------------------------------------------
 // dispatch helpers
 // ---------------------------------------------------------------------------
@@ -848,6 +883,21 @@ void xcu_array_op(void *stream, void *out, const void *in, size_t n, int xdom, i
 #define X(T, OP, MODE) k_array<T, OP><<<nb, 256, 0, st>>>((T *)out, (const T *)in, n)
   FOR_ALL(X)
 #undef X
+  LAUNCHED();
+}
+
+/* out (device, 1 double) = sum v[i]*w[i]; scratch holds at least xcu_dot_parts() doubles.
+   v and w must be 16-byte aligned device pointers (checked by the caller).   */
+unsigned xcu_dot_parts(void) { return 148u * 8u; }
+void xcu_dot(void *stream, const double *v, const double *w, size_t n, double *scratch, double *out)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned nb = (unsigned)((n / 2 + DOT_THREADS - 1) / DOT_THREADS);
+  if (nb > xcu_dot_parts()) nb = xcu_dot_parts();
+  if (nb == 0) nb = 1;
+  k_dot_partial<<<nb, DOT_THREADS, 0, st>>>(v, w, n, scratch);
+  LAUNCHED();
+  k_dot_final<<<1, 1, 0, st>>>(scratch, nb, out);
   LAUNCHED();
 }
 

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     L.exags_comm_barrier.argtypes = [comm_ptr]
     L.exags_comm_allreduce.argtypes = [comm_ptr, i32, i32, vp, u32, vp]
     L.exags_comm_scan.argtypes = [vp, comm_ptr, i32, i32, vp, u32, vp]
+    L.exags_comm_dot.argtypes = [comm_ptr, vp, vp, u32]
+    L.exags_comm_dot.restype = C.c_double
     L.gslib_gs_setup.argtypes = [vp, u32, comm_ptr, i32, i32, i32]
     L.gslib_gs_setup.restype = vp
     L.exags_gs_setup.argtypes = [vp, u32, comm_ptr, i32, i32, i32]
@@ -231,6 +233,18 @@ def gs_unique(ids: np.ndarray, comm=None) -> None:
 def exchange_transport() -> str:
     """'single' | 'push' | 'nccl' | 'ipc' (include/exags_cuda.h)."""
     return lib().exags_exchange_transport().decode()
+
+
+def comm_dot(v, w, comm=None) -> float:
+    """comm_dot(cp, v, w, n) (src/comm.upc:954): v, w host arrays or device tensors of doubles."""
+    n = v.numel() if hasattr(v, "numel") else v.size
+    return float(lib().exags_comm_dot(comm if comm is not None else comm_world(), _addr(v), _addr(w), n))
+
+
+def comm_allreduce(v, dom: int, op: int, comm=None) -> None:
+    """comm_allreduce(cp, dom, op, v, vn, buf) in place (src/comm.upc:831)."""
+    n = v.numel() if hasattr(v, "numel") else v.size
+    lib().exags_comm_allreduce(comm if comm is not None else comm_world(), dom, op, _addr(v), n, None)
 
 
 def kernel_launches() -> int:

@@ -198,7 +198,8 @@ void exags_comm_time(double *tm);                     /* comm.upc:411 */
 void exags_comm_barrier(const comm_ptr cp);           /* comm.upc:420 */
 void exags_comm_bcast(const comm_ptr cp, void *p, size_t n, exags_uint root);
                                                       /* comm.upc:427 */
-/* v (host) <- OP over ranks, element-wise; buf is scratch of the same size.
+/* v <- OP over ranks, element-wise; buf is scratch of the same size (unused).
+   v may be a host vector (the reference's contract) or a device vector.
    Replaces comm_allreduce() src/comm.upc:831-950                           */
 void exags_comm_allreduce(const comm_ptr cp, gs_dom dom, gs_op_t op,
                           void *v, exags_uint vn, void *buf);
@@ -206,6 +207,8 @@ void exags_comm_allreduce(const comm_ptr cp, gs_dom dom, gs_op_t op,
    Replaces comm_scan() src/comm.upc:706-801                                */
 void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
                      const void *v, exags_uint vn, void *buffer);
+/* sum over ranks of v.w; v and w both host vectors, or both 16-byte aligned
+   device vectors (then the local part is an HBM-bound reduction kernel).   */
 double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n);
                                                       /* comm.upc:954 */
 /* Element type tags for the Fortran-facing reductions (the reference hands

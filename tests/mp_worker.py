@@ -154,6 +154,23 @@ def main():
                             print(f"MISMATCH exec2 it={it} handle={hid} rank={r}")
                             ok = False
         X.gs_free(gb)
+        # comm_dot / comm_allreduce on device vectors across ranks
+        rng = np.random.default_rng(40 + rank)
+        a, b = rng.integers(-8, 9, 50001).astype(np.float64), rng.integers(-8, 9, 50001).astype(np.float64)
+        got = X.comm_dot(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+        parts = gather_arrays(float(np.dot(a, b)), np_)
+        if got != float(sum(parts)):
+            print(f"MISMATCH comm_dot rank={rank}: {got} vs {sum(parts)}")
+            ok = False
+        for n_el in (5, 300000):                              # host-folded and NCCL-sized vectors
+            iv = rng.integers(-1000, 1000, n_el).astype(np.int64)
+            dv = torch.from_numpy(iv.copy()).cuda()
+            X.comm_allreduce(dv, X.gs_long, X.gs_max)
+            alls = gather_arrays(iv, np_)
+            if not np.array_equal(dv.cpu().numpy(), np.max(np.stack(alls), axis=0)):
+                print(f"MISMATCH device comm_allreduce n={n_el} rank={rank}")
+                ok = False
+        okt = torch.tensor([1 if ok else 0]); dist.all_reduce(okt, op=dist.ReduceOp.MIN); ok = bool(okt.item())
     flag = torch.tensor([0 if ok else 1])
     dist.broadcast(flag, 0)
     X.gs_free(g)

@@ -410,3 +410,21 @@ def test_c_caller_links_and_runs(X, tmp_path):
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "EXAGS_HOST_SETUP_ONLY")}
         r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=120)
         assert r.returncode == 0 and "caller_run ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_comm_dot_device_vectors(X):
+    """comm_dot on device vectors: exact when every partial sum is an integer
+    below 2^53 (any association gives the same bits), within rounding otherwise;
+    odd lengths and the empty vector included."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 4096, 1_000_003):
+        v = rng.integers(-8, 9, n).astype(np.float64)
+        w = rng.integers(-8, 9, n).astype(np.float64)
+        want = float(np.dot(v, w))
+        assert X.comm_dot(v, w) == want                     # host vectors (reference path)
+        if n:
+            assert X.comm_dot(_dev(v), _dev(w)) == want     # device vectors
+    v, w = rng.uniform(-1, 1, 3_000_001), rng.uniform(-1, 1, 3_000_001)
+    got, want = X.comm_dot(_dev(v), _dev(w)), float(np.dot(v, w))
+    scale = float(np.dot(np.abs(v), np.abs(w)))
+    assert abs(got - want) <= 64 * np.finfo(np.float64).eps * scale

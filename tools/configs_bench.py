@@ -72,6 +72,19 @@ run("gs_vec(3,add,double)", X.mode_vec, 3, X.gs_double, X.gs_add)
 run("gs_vec(3,add,float)", X.mode_vec, 3, X.gs_float, X.gs_add)
 run("gs_many(3,add,double)", X.mode_many, 3, X.gs_double, X.gs_add)
 run("gs_many(3,add,float)", X.mode_many, 3, X.gs_float, X.gs_add)
+# comm_dot on two device vectors of n doubles: 16 B per element, HBM-bound
+va, vb = torch.ones(n, dtype=torch.float64, device="cuda"), torch.full((n,), 0.5, dtype=torch.float64, device="cuda")
+for _ in range(3):
+    X.comm_dot(va, vb)
+import time as _t
+torch.cuda.synchronize(); t0 = _t.perf_counter()
+for _ in range(args.steps):
+    r = X.comm_dot(va, vb)
+ms = 1e3 * (_t.perf_counter() - t0) / args.steps
+assert r == 0.5 * n
+print(f"{'comm_dot(device, n doubles)':34s} {ms:8.4f} ms  (blocking call incl. the scalar D2H)  "
+      f"{16 * n / ms / 1e6:7.0f} GB/s  frac {16 * n / ms / 1e6 / peak:.3f}", flush=True)
+del va, vb
 X.gs_free(g)
 # flagged labels -> CSR path with per-group unflagged counts
 ids2 = ids.copy()

@@ -1,5 +1,7 @@
-"""Run bench.py under several kernel/layout knobs and print one line each.
-Tuning aid for the GPU box:  python tools/sweep.py 'LAYOUT=csr' 'VARIANT=0,TILE=2048' ..."""
+"""Run bench.py under several library knobs and print one line each.
+Tuning aid for the GPU box:  python tools/sweep.py 'LAYOUT=csr' 'LAYOUT=sell' 'PIPE=0' ...
+(the VARIANT / CTAS / SIGMA knobs of earlier sweeps -- profiles/r1_sweep*.txt -- selected kernel
+variants that have since been removed; they are ignored by the library now)"""
 import json
 import os
 import subprocess
@@ -10,7 +12,8 @@ for spec in sys.argv[1:]:
     env = dict(os.environ)
     for kv in spec.split(","):
         k, v = kv.split("=")
-        env[{"LAYOUT": "EXAGS_LAYOUT", "VARIANT": "EXAGS_SELL_VARIANT", "SIGMA": "EXAGS_SELL_SIGMA", "CTAS": "EXAGS_SELL_CTAS"}[k]] = v
+        env[{"LAYOUT": "EXAGS_LAYOUT", "PIPE": "EXAGS_HOST_PIPELINE", "CHUNK": "EXAGS_PIPE_CHUNK_BYTES",
+             "VARIANT": "EXAGS_SELL_VARIANT", "SIGMA": "EXAGS_SELL_SIGMA", "CTAS": "EXAGS_SELL_CTAS"}[k]] = v
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "3", "--no-cpu"],
                        env=env, capture_output=True, text=True)
     try:
