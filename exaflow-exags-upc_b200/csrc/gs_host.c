@@ -91,10 +91,21 @@ static u64 count_sectors(const struct xg_hmap *m, unsigned elem_bytes)
   u64 cnt = 0;
   if (!m->ni) return 0;
   u32 maxi = 0;
+  const int nthr = xg_setup_threads();
+  (void)nthr;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(max : maxi) num_threads(nthr)
+#endif
   for (u32 k = 0; k < m->ni; ++k) if (m->idx[k] > maxi) maxi = m->idx[k];
   size_t nsec = ((size_t)maxi * elem_bytes) / 32 + 1;
   unsigned char *mark = xnew0(unsigned char, nsec);
-  for (u32 k = 0; k < m->ni; ++k) mark[((size_t)m->idx[k] * elem_bytes) / 32] = 1;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthr)
+#endif
+  for (u32 k = 0; k < m->ni; ++k) mark[((size_t)m->idx[k] * elem_bytes) / 32] = 1;   /* same value from every writer */
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : cnt) num_threads(nthr)
+#endif
   for (size_t s = 0; s < nsec; ++s) cnt += mark[s];
   free(mark);
   return cnt;
@@ -636,15 +647,37 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   const u32 nb = pl->nb;
   int any_flag = g->hall.nunf != 0;
   struct xg_hmap in; memset(&in, 0, sizeof in);
-  size_t ng = 0, ni = 0, nfs = 0, bni = 0;
-  {
-    u32 b = 0;
-    for (size_t gi = 0; gi < t->ngrp; ++gi) {
+  /* two chunked passes over the label groups (count, prefix, fill): the output
+     keeps the serial order and the chunks spread over the host cores */
+  enum { NCH = 256 };
+  size_t cg[NCH], ci[NCH], cf[NCH], cb[NCH], cbi[NCH];
+  const int nthr = xg_setup_threads();
+  (void)nthr;
+#define GLO(c) ((size_t)t->ngrp * (size_t)(c) / NCH)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthr)
+#endif
+  for (int c = 0; c < NCH; ++c) {
+    size_t ng_ = 0, ni_ = 0, nf_ = 0, bni_ = 0;
+    /* first boundary primary whose group lies in this chunk (bgrp ascends) */
+    u32 lo = 0, hi = nb;
+    while (lo < hi) { u32 mid = lo + (hi - lo) / 2; if (pl->bgrp[mid] < GLO(c)) lo = mid + 1; else hi = mid; }
+    u32 bb = lo;
+    for (size_t gi = GLO(c); gi < GLO(c + 1); ++gi) {
       u32 a = t->gstart[gi], e = t->gstart[gi + 1];
-      if (b < nb && pl->bgrp[b] == gi) { ++b; bni += e - a; continue; }
-      if (e - a >= 2) { ++ng; ni += e - a; }
-      else if (t->flag[a]) ++nfs;
+      if (bb < nb && pl->bgrp[bb] == gi) { ++bb; bni_ += e - a; continue; }
+      if (e - a >= 2) { ++ng_; ni_ += e - a; }
+      else if (t->flag[a]) ++nf_;
     }
+    cg[c] = ng_; ci[c] = ni_; cf[c] = nf_; cb[c] = lo; cbi[c] = bni_;
+  }
+  size_t ng = 0, ni = 0, nfs = 0, bni = 0;
+  for (int c = 0; c < NCH; ++c) {
+    size_t v;
+    v = cg[c]; cg[c] = ng; ng += v;
+    v = ci[c]; ci[c] = ni; ni += v;
+    v = cf[c]; cf[c] = nfs; nfs += v;
+    v = cbi[c]; cbi[c] = bni; bni += v;
   }
   in.ng = (u32)ng; in.ni = (u32)ni;
   in.off = xnew(u32, ng + 1);
@@ -652,11 +685,14 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   if (any_flag) in.nunf = xnew(u32, ng ? ng : 1);
   u32 *fs = xnew(u32, nfs ? nfs : 1);
   u32 *bgoff = xnew(u32, (size_t)nb + 1), *bgidx = xnew(u32, bni ? bni : 1), *bnunf = xnew(u32, nb ? nb : 1);
-  {
-    u32 b = 0; size_t og = 0, oi = 0, of = 0, ob = 0;
-    for (size_t gi = 0; gi < t->ngrp; ++gi) {
-      u32 a = t->gstart[gi], e = t->gstart[gi + 1], unf = 0;
-      for (u32 j = a; j < e && !t->flag[j]; ++j) ++unf;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthr)
+#endif
+  for (int c = 0; c < NCH; ++c) {
+    u32 b = (u32)cb[c]; size_t og = cg[c], oi = ci[c], of = cf[c], ob = cbi[c];
+    for (size_t gi = GLO(c); gi < GLO(c + 1); ++gi) {
+      u32 a = t->gstart[gi], e = t->gstart[gi + 1], unf = e - a;
+      if (any_flag) { unf = 0; for (u32 j = a; j < e && !t->flag[j]; ++j) ++unf; }
       if (b < nb && pl->bgrp[b] == gi) {
         bgoff[b] = (u32)ob; bnunf[b] = unf;
         memcpy(bgidx + ob, t->idx + a, (size_t)(e - a) * sizeof(u32));
@@ -670,9 +706,10 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
         oi += e - a; ++og;
       } else if (t->flag[a]) fs[of++] = t->idx[a];
     }
-    in.off[ng] = (u32)oi;
-    bgoff[nb] = (u32)ob;
   }
+#undef GLO
+  in.off[ng] = (u32)ni;
+  bgoff[nb] = (u32)bni;
   g->nfs = (u32)nfs;
   /* symmetric maps take the sliced-ELL layout (EXAGS_LAYOUT=csr keeps CSR) */
   struct xg_sell sell; memset(&sell, 0, sizeof sell);

@@ -39,80 +39,133 @@ static unsigned nbits64(u64 v)
   return b ? b : 1;
 }
 
+/* The setup loops below run over 10^8 rows; each is cut into XG_CHUNKS
+   contiguous chunks handled in two passes (count per chunk, exclusive prefix,
+   fill at the chunk's offset), so the output order is the serial order and the
+   chunks can be spread over the host cores.                                 */
+#define XG_CHUNKS 256
+#define CHUNK_LO(n, c) ((size_t)(n) * (size_t)(c) / XG_CHUNKS)
+#ifdef _OPENMP
+#define PAR_CHUNKS _Pragma("omp parallel for schedule(dynamic, 1) num_threads(xg_setup_threads())")
+#else
+#define PAR_CHUNKS
+#endif
+
+static size_t prefix_chunks(size_t *cnt)       /* exclusive prefix in place; returns the total */
+{
+  size_t run = 0;
+  for (int c = 0; c < XG_CHUNKS; ++c) { size_t v = cnt[c]; cnt[c] = run; run += v; }
+  return run;
+}
+
 void xg_topo_build(struct xg_topo *t, const i64 *id, size_t n)
 {
   memset(t, 0, sizeof *t);
   if (n >= (size_t)XG_NONE)
     xfail("gs_setup: local size %lu does not fit the 32-bit index type", (unsigned long)n);
+  size_t cnt[XG_CHUNKS], cnt2[XG_CHUNKS];
+  u64 cmax[XG_CHUNKS];
 
   /* rows for nonzero labels: key = |id|*2 + flagged, payload = index */
-  size_t nnz = 0;
-  for (size_t i = 0; i < n; ++i) nnz += (id[i] != 0);
-  u64 *key = xnew(u64, nnz), *tk = xnew(u64, nnz);
-  u32 *val = xnew(u32, nnz), *tv = xnew(u32, nnz);
-  u64 maxkey = 0;
-  size_t r = 0;
-  for (size_t i = 0; i < n; ++i) {
-    i64 v = id[i];
-    if (v == 0) continue;
-    u64 a = v < 0 ? (u64)(-(v + 1)) + 1u : (u64)v;
-    if (a >> 62) xfail("gs_setup: |id| = %llu is too large", (unsigned long long)a);
-    u64 k = (a << 1) | (u64)(v < 0);
-    key[r] = k; val[r] = (u32)i; ++r;
-    if (k > maxkey) maxkey = k;
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t k = 0;
+    for (size_t i = CHUNK_LO(n, c); i < CHUNK_LO(n, c + 1); ++i) k += (id[i] != 0);
+    cnt[c] = k;
   }
+  const size_t nnz = prefix_chunks(cnt);
+  u64 *key = xnew(u64, nnz ? nnz : 1), *tk = xnew(u64, nnz ? nnz : 1);
+  u32 *val = xnew(u32, nnz ? nnz : 1), *tv = xnew(u32, nnz ? nnz : 1);
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t r = cnt[c];
+    u64 mx = 0;
+    for (size_t i = CHUNK_LO(n, c); i < CHUNK_LO(n, c + 1); ++i) {
+      i64 v = id[i];
+      if (v == 0) continue;
+      u64 a = v < 0 ? (u64)(-(v + 1)) + 1u : (u64)v;
+      u64 k = (a << 1) | (u64)(v < 0);
+      key[r] = k; val[r] = (u32)i; ++r;
+      if (a > mx) mx = a;
+    }
+    cmax[c] = mx;
+  }
+  u64 maxabs = 0;
+  for (int c = 0; c < XG_CHUNKS; ++c) if (cmax[c] > maxabs) maxabs = cmax[c];
+  if (maxabs >> 62) xfail("gs_setup: |id| = %llu is too large", (unsigned long long)maxabs);
   /* (|id|, flag) ascending; stable => ascending index inside each class */
-  xsort_u64_u32(key, val, nnz, nbits64(maxkey), tk, tv);
+  xsort_u64_u32(key, val, nnz, nbits64((maxabs << 1) | 1u), tk, tv);
   free(tk); free(tv);
 
-  /* label groups in label order */
-  size_t ngrp = 0;
-  for (size_t j = 0; j < nnz; ++j)
-    ngrp += (j == 0 || (key[j] >> 1) != (key[j - 1] >> 1));
-  u32 *gs0 = xnew(u32, ngrp + 1);
-  u32 *prim = xnew(u32, ngrp ? ngrp : 1);
-  u32 maxprim = 0;
-  {
-    size_t g = 0;
-    for (size_t j = 0; j < nnz; ++j)
-      if (j == 0 || (key[j] >> 1) != (key[j - 1] >> 1)) {
-        gs0[g] = (u32)j; prim[g] = val[j];
-        if (val[j] > maxprim) maxprim = val[j];
-        ++g;
-      }
-    gs0[ngrp] = (u32)nnz;
+  /* label groups in label order: row j heads a group when its label differs
+     from the row before */
+#define IS_HEAD(j) ((j) == 0 || (key[j] >> 1) != (key[(j) - 1] >> 1))
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t k = 0;
+    for (size_t j = CHUNK_LO(nnz, c); j < CHUNK_LO(nnz, c + 1); ++j) k += IS_HEAD(j);
+    cnt[c] = k;
   }
-  /* order the groups by primary index (primaries are distinct) */
+  const size_t ngrp = prefix_chunks(cnt);
+  u32 *gs0 = xnew(u32, ngrp + 1);
+  /* order the groups by primary index.  Primaries are distinct local indices,
+     so one table over the indices replaces a sort: slot[primary] = group, then
+     the occupied slots are read off in ascending order                       */
+  u32 *slot = xnew(u32, n ? n : 1);
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c)
+    for (size_t i = CHUNK_LO(n, c); i < CHUNK_LO(n, c + 1); ++i) slot[i] = XG_NONE;
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t g = cnt[c];
+    for (size_t j = CHUNK_LO(nnz, c); j < CHUNK_LO(nnz, c + 1); ++j)
+      if (IS_HEAD(j)) { gs0[g] = (u32)j; slot[val[j]] = (u32)g; ++g; }
+  }
+#undef IS_HEAD
+  gs0[ngrp] = (u32)nnz;
   u32 *order = xnew(u32, ngrp ? ngrp : 1);
-  for (size_t g = 0; g < ngrp; ++g) order[g] = (u32)g;
-  xsort_perm_u32(order, prim, ngrp, maxprim);
-  free(prim);
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t k = 0;
+    for (size_t i = CHUNK_LO(n, c); i < CHUNK_LO(n, c + 1); ++i) k += (slot[i] != XG_NONE);
+    cnt2[c] = k;
+  }
+  prefix_chunks(cnt2);
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t o = cnt2[c];
+    for (size_t i = CHUNK_LO(n, c); i < CHUNK_LO(n, c + 1); ++i)
+      if (slot[i] != XG_NONE) order[o++] = slot[i];
+  }
+  free(slot);
 
   t->nnz = nnz; t->ngrp = ngrp;
   t->id = xnew(u64, ngrp ? ngrp : 1);
   t->idx = xnew(u32, nnz ? nnz : 1);
   t->flag = xnew(unsigned char, nnz ? nnz : 1);
   t->gstart = xnew(u32, ngrp + 1);
-  {
-    u32 run = 0;
-    for (size_t g = 0; g < ngrp; ++g) {
-      u32 s = order[g];
-      t->gstart[g] = run;
-      run += gs0[s + 1] - gs0[s];
-    }
-    t->gstart[ngrp] = run;
+  /* row offset of every group in the new order */
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t k = 0;
+    for (size_t g = CHUNK_LO(ngrp, c); g < CHUNK_LO(ngrp, c + 1); ++g) k += gs0[order[g] + 1] - gs0[order[g]];
+    cnt[c] = k;
   }
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static) num_threads(xg_setup_threads())
-#endif
-  for (size_t g = 0; g < ngrp; ++g) {
-    u32 s = order[g], a = gs0[s], b = gs0[s + 1], o = t->gstart[g];
-    t->id[g] = key[a] >> 1;
-    for (u32 j = a; j < b; ++j, ++o) {
-      t->idx[o] = val[j];
-      t->flag[o] = (unsigned char)(key[j] & 1u);
+  prefix_chunks(cnt);
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    u32 o = (u32)cnt[c];
+    for (size_t g = CHUNK_LO(ngrp, c); g < CHUNK_LO(ngrp, c + 1); ++g) {
+      const u32 s = order[g], a = gs0[s], b = gs0[s + 1];
+      t->gstart[g] = o;
+      t->id[g] = key[a] >> 1;
+      for (u32 j = a; j < b; ++j, ++o) {
+        t->idx[o] = val[j];
+        t->flag[o] = (unsigned char)(key[j] & 1u);
+      }
     }
   }
+  t->gstart[ngrp] = (u32)nnz;
   free(order); free(gs0); free(key); free(val);
 }
 
@@ -123,33 +176,48 @@ void xg_topo_build(struct xg_topo *t, const i64 *id, size_t n)
 void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m)
 {
   memset(m, 0, sizeof *m);
-  int any_flag = 0;
-  for (size_t j = 0; j < t->nnz && !any_flag; ++j) any_flag = t->flag[j];
-  size_t ng = 0, ni = 0;
-  for (size_t g = 0; g < t->ngrp; ++g) {
-    u32 a = t->gstart[g], b = t->gstart[g + 1], cnt = 1;
-    if (all) cnt = b - a;
-    else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++cnt;
-    if (cnt >= 2) { ++ng; ni += cnt; }
+  size_t cg[XG_CHUNKS], ci[XG_CHUNKS], cf[XG_CHUNKS];
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t f = 0;
+    for (size_t j = CHUNK_LO(t->nnz, c); j < CHUNK_LO(t->nnz, c + 1) && !f; ++j) f = t->flag[j];
+    cf[c] = f;
   }
+  int any_flag = 0;
+  for (int c = 0; c < XG_CHUNKS; ++c) any_flag |= cf[c] != 0;
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t ng = 0, ni = 0;
+    for (size_t g = CHUNK_LO(t->ngrp, c); g < CHUNK_LO(t->ngrp, c + 1); ++g) {
+      u32 a = t->gstart[g], b = t->gstart[g + 1], k = 1;
+      if (all) k = b - a;
+      else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++k;
+      if (k >= 2) { ++ng; ni += k; }
+    }
+    cg[c] = ng; ci[c] = ni;
+  }
+  const size_t ng = prefix_chunks(cg), ni = prefix_chunks(ci);
   if (ni >= (size_t)XG_NONE) xfail("gs_setup: local map too large");
   m->ng = (u32)ng; m->ni = (u32)ni;
   m->off = xnew(u32, ng + 1);
   m->idx = xnew(u32, ni ? ni : 1);
   if (all && any_flag) m->nunf = xnew(u32, ng ? ng : 1);
-  size_t og = 0, oi = 0;
-  for (size_t g = 0; g < t->ngrp; ++g) {
-    u32 a = t->gstart[g], b = t->gstart[g + 1], cnt = 1, unf = 0;
-    for (u32 j = a; j < b && !t->flag[j]; ++j) ++unf;
-    if (all) cnt = b - a;
-    else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++cnt;
-    if (cnt < 2) continue;
-    m->off[og] = (u32)oi;
-    if (m->nunf) m->nunf[og] = unf;
-    memcpy(m->idx + oi, t->idx + a, (size_t)cnt * sizeof(u32));
-    oi += cnt; ++og;
+  PAR_CHUNKS
+  for (int c = 0; c < XG_CHUNKS; ++c) {
+    size_t og = cg[c], oi = ci[c];
+    for (size_t g = CHUNK_LO(t->ngrp, c); g < CHUNK_LO(t->ngrp, c + 1); ++g) {
+      u32 a = t->gstart[g], b = t->gstart[g + 1], k = 1, unf = 0;
+      if (any_flag) for (u32 j = a; j < b && !t->flag[j]; ++j) ++unf;
+      if (all) k = b - a;
+      else for (u32 j = a + 1; j < b && !t->flag[j]; ++j) ++k;
+      if (k < 2) continue;
+      m->off[og] = (u32)oi;
+      if (m->nunf) m->nunf[og] = unf;
+      memcpy(m->idx + oi, t->idx + a, (size_t)k * sizeof(u32));
+      oi += k; ++og;
+    }
   }
-  m->off[ng] = (u32)oi;
+  m->off[ng] = (u32)ni;
 }
 
 /* indices of primaries whose label is flagged (src/gs.upc:359-370); when
