@@ -250,6 +250,36 @@ void xg_host_allgather(struct xg_world *w, const void *in, size_t bytes, void *o
   pub_destroy(w, mine, bytes);
 }
 
+/* Label-presence bitmaps of gs_setup.  xg_host_bitmap_new returns this rank's
+   bitmap inside a fresh shared segment (zero-filled by the OS, so there is
+   nothing to clear or copy); xg_host_bitmap_or_others then fills others[k] with
+   the OR of every OTHER rank's word k and releases the segment.  `words` is the
+   same on every rank.                                                        */
+u64 *xg_host_bitmap_new(struct xg_world *w, size_t words)
+{
+  if (w->np == 1) return xnew0(u64, words);
+  return (u64 *)pub_create(w, words * sizeof(u64));
+}
+
+void xg_host_bitmap_or_others(struct xg_world *w, u64 *mine, size_t words, u64 *others)
+{
+  memset(others, 0, words * sizeof(u64));
+  if (w->np == 1) { free(mine); return; }
+  xg_host_barrier(w);
+  for (int p = 0; p < w->np; ++p) {
+    if (p == w->rank) continue;
+    size_t pb;
+    const u64 *q = (const u64 *)pub_peer(w, p, &pb);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(xg_setup_threads())
+#endif
+    for (size_t k = 0; k < words; ++k) others[k] |= q[k];
+    munmap((void *)q, pb ? pb : 1);
+  }
+  xg_host_barrier(w);
+  pub_destroy(w, mine, words * sizeof(u64));
+}
+
 void *xg_host_alltoallv(struct xg_world *w, const void *rows, size_t rowbytes,
                         const size_t *sendcnt, size_t *recvcnt, size_t *nrecv)
 {

@@ -168,6 +168,8 @@ void  xg_mbox_free(struct xg_world *w, struct xg_mbox *mb);
 void  xg_host_barrier(struct xg_world *w);
 /* every rank contributes `bytes` bytes; out receives np*bytes, rank-major   */
 void  xg_host_allgather(struct xg_world *w, const void *in, size_t bytes, void *out);
+u64  *xg_host_bitmap_new(struct xg_world *w, size_t words);
+void  xg_host_bitmap_or_others(struct xg_world *w, u64 *mine, size_t words, u64 *others);
 /* rows of `rowbytes` bytes, already grouped by destination: sendcnt[p] rows
    go to rank p.  Returns a malloc'd array of received rows ordered by source
    rank; *nrecv rows, recvcnt[p] (caller array of np) from each source.      */
