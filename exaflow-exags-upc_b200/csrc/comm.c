@@ -399,14 +399,16 @@ static int nccl_op(int xop)
   return 0;
 }
 
-void xg_nccl_group_start(struct xg_world *w) { (void)w; NC(nc.GroupStart()); }
+void xg_nccl_group_start(struct xg_world *w) { (void)xg_world_nccl(w); NC(nc.GroupStart()); }
 void xg_nccl_group_end(struct xg_world *w)   { (void)w; NC(nc.GroupEnd()); }
+/* the communicator is created (and the library loaded) on first use: fetch it
+   before the function pointer is read */
 void xg_nccl_send(struct xg_world *w, const void *buf, size_t count, int xd, int peer, void *stream)
-{ NC(nc.Send(buf, count, nccl_dtype(xd), peer, xg_world_nccl(w), stream)); }
+{ void *c = xg_world_nccl(w); NC(nc.Send(buf, count, nccl_dtype(xd), peer, c, stream)); }
 void xg_nccl_recv(struct xg_world *w, void *buf, size_t count, int xd, int peer, void *stream)
-{ NC(nc.Recv(buf, count, nccl_dtype(xd), peer, xg_world_nccl(w), stream)); }
+{ void *c = xg_world_nccl(w); NC(nc.Recv(buf, count, nccl_dtype(xd), peer, c, stream)); }
 void xg_nccl_allreduce(struct xg_world *w, void *buf, size_t count, int xd, int xop, void *stream)
-{ NC(nc.AllReduce(buf, buf, count, nccl_dtype(xd), nccl_op(xop), xg_world_nccl(w), stream)); }
+{ void *c = xg_world_nccl(w); NC(nc.AllReduce(buf, buf, count, nccl_dtype(xd), nccl_op(xop), c, stream)); }
 
 /* ------------------------------------------------------------------ */
 /*  world                                                              */

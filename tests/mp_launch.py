@@ -17,7 +17,7 @@ def run_ranks(np_, args, timeout=300, extra_env=None):
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EXAGS_JOB_KEY=key,
                    OMP_NUM_THREADS="2")
         env.update(extra_env or {})
-        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mp_worker.py")] + [str(a) for a in args],
+        procs.append(subprocess.Popen([sys.executable, "-X", "faulthandler", os.path.join(HERE, "mp_worker.py")] + [str(a) for a in args],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs, codes = [], []
     for p in procs:

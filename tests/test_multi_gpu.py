@@ -25,7 +25,7 @@ def test_multirank_exec_nccl(built, np_, case, method, transport):
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "exec", 0, method], timeout=600,
                             extra_env={"EXAGS_EXCHANGE": transport})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks"), (8, "blocks"), (3, "empty")])
@@ -35,7 +35,7 @@ def test_multirank_auto_method(built, np_, case):
     if _ndev() < np_:
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "exec", 0, 0], timeout=600)
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
@@ -43,7 +43,7 @@ def test_multirank_exec_unique(built, np_, case):
     if _ndev() < np_:
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "exec", 1, 1], timeout=600)
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case,method,unique", [(2, "slab", 1, 0), (3, "random", 1, 0), (4, "blocks", 1, 0),
@@ -58,7 +58,7 @@ def test_multirank_exec_one_gpu(built, np_, case, method, unique):
         pytest.skip("needs a GPU")
     codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0"})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case,method,unique", [(2, "slab", 1, 0), (3, "random", 1, 0), (4, "blocks", 1, 0),
@@ -73,7 +73,7 @@ def test_multirank_exec_one_gpu_push(built, np_, case, method, unique):
         pytest.skip("needs a GPU")
     codes, outs = run_ranks(np_, [case, "exec", unique, method], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": "push"})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case,transport", [(2, "slab", "ipc"), (4, "blocks", "push"), (2, "random", "ipc"),
@@ -88,7 +88,7 @@ def test_multirank_host_pointers_one_gpu(built, np_, case, transport):
     codes, outs = run_ranks(np_, [case, "exech", 0, 1], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": transport,
                                        "EXAGS_PIPE_CHUNK_BYTES": "512"})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
@@ -97,7 +97,7 @@ def test_multirank_host_pointers(built, np_, case):
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "exech", 0, 1], timeout=600,
                             extra_env={"EXAGS_PIPE_CHUNK_BYTES": "512"})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 @pytest.mark.parametrize("np_,transport", [(3, "push"), (4, "push"), (2, "ipc")])
@@ -109,11 +109,11 @@ def test_two_handles_interleaved_one_gpu(built, np_, transport):
         pytest.skip("needs a GPU")
     codes, outs = run_ranks(np_, ["blocks", "exec2", 0, 1], timeout=900,
                             extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": transport})
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
 
 
 def test_two_handles_interleaved(built):
     if _ndev() < 4:
         pytest.skip(f"needs 4 GPUs, have {_ndev()}")
     codes, outs = run_ranks(4, ["blocks", "exec2", 0, 1], timeout=600)
-    assert all(c == 0 for c in codes), "\n".join(outs)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
