@@ -24,6 +24,10 @@ def make_ids(case, np_, rank):
         return cases.gs_test_fixture_ids(np_, rank)
     if case == "slab":
         return semmesh.box_ids(3, 3, 2, 3, ez0=2 * rank, Ez_global=2 * np_)
+    if case == "bigslab":    # large enough for every chunk of the parallel setup loops to hold rows
+        return semmesh.box_ids(12, 10, 3, 5, ez0=3 * rank, Ez_global=3 * np_)
+    if case == "bigblocks":
+        return semmesh.block_partition_ids(8, 8, 8, 4, 2, 2, 2, np_, rank)[0]
     if case == "blocks":
         return semmesh.block_partition_ids(4, 4, 4, 2, 2, 2, 2, np_, rank)[0]
     if case == "random":
