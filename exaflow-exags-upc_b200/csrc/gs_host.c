@@ -215,7 +215,7 @@ static void push_prepare(struct gs_data *g, size_t data_bytes)
 static double push_timeout(void)
 {
   static double t = -1;
-  if (t < 0) { const char *v = getenv("EXAGS_PUSH_TIMEOUT_S"); t = v && atof(v) > 0 ? atof(v) : 20.0; }
+  if (t < 0) { const char *v = getenv("EXAGS_PUSH_TIMEOUT_S"); t = v && atof(v) > 0 ? atof(v) : 60.0; }
   return t;
 }
 
