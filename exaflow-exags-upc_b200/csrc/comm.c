@@ -789,6 +789,24 @@ double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n)
   return s;
 }
 
+/* T comm_reduce__T(cp, op, in, n): fold a local host array, then across ranks
+   (src/comm.upc:961-984).                                              */
+#define DEFINE_REDUCE(T, NAME, DOM)                                           \
+  T exags_comm_reduce__##NAME(const comm_ptr cp, gs_op_t op, const T *in, exags_uint n) \
+  {                                                                           \
+    T accum, buf;                                                             \
+    host_identity(&accum, 1, xg_dom_of(DOM), (int)op);                        \
+    for (exags_uint i = 0; i < n; ++i) host_combine(&accum, in + i, 1, xg_dom_of(DOM), (int)op); \
+    exags_comm_allreduce(cp, (gs_dom)DOM, op, &accum, 1, &buf);               \
+    return accum;                                                             \
+  }
+DEFINE_REDUCE(double, double, gs_double)
+DEFINE_REDUCE(float, float, gs_float)
+DEFINE_REDUCE(int, int, gs_int)
+DEFINE_REDUCE(long, long, gs_long)
+DEFINE_REDUCE(long long, long_long, 4)
+#undef DEFINE_REDUCE
+
 /* ------------------------------------------------------------------ */
 /*  element type tags and Fortran bindings (src/comm.upc:376-407,       */
 /*  804-827, 1031-1148)                                                 */

@@ -211,6 +211,12 @@ void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
    device vectors (then the local part is an HBM-bound reduction kernel).   */
 double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n);
                                                       /* comm.upc:954 */
+/* fold a local host array with op, then across ranks (comm.upc:961-984)    */
+double    exags_comm_reduce__double(const comm_ptr cp, gs_op_t op, const double *in, exags_uint n);
+float     exags_comm_reduce__float(const comm_ptr cp, gs_op_t op, const float *in, exags_uint n);
+int       exags_comm_reduce__int(const comm_ptr cp, gs_op_t op, const int *in, exags_uint n);
+long      exags_comm_reduce__long(const comm_ptr cp, gs_op_t op, const long *in, exags_uint n);
+long long exags_comm_reduce__long_long(const comm_ptr cp, gs_op_t op, const long long *in, exags_uint n);
 /* Element type tags for the Fortran-facing reductions (the reference hands
    out upc_type_t values, src/comm.h:72, src/comm.upc:376-400; callers only
    ever obtain them from these four functions).                             */
@@ -306,6 +312,17 @@ void fgslib_gs_free_(const int *handle);
 # define comm_allreduce exags_comm_allreduce
 # define comm_scan      exags_comm_scan
 # define comm_dot       exags_comm_dot
+# define comm_reduce_double    exags_comm_reduce__double
+# define comm_reduce_float     exags_comm_reduce__float
+# define comm_reduce_int       exags_comm_reduce__int
+# define comm_reduce_long      exags_comm_reduce__long
+# define comm_reduce_long_long exags_comm_reduce__long_long
+# define comm_reduce_sint      exags_comm_reduce__int        /* comm.h:216-219 */
+# ifdef EXAGS_NEK
+#  define comm_reduce_slong    exags_comm_reduce__long_long
+# else
+#  define comm_reduce_slong    exags_comm_reduce__int
+# endif
 # define comm_type_int  exags_comm_type_int
 # define comm_type_int8 exags_comm_type_int8
 # define comm_type_real exags_comm_type_real

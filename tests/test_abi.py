@@ -71,6 +71,29 @@ def test_fortran_comm_bindings_single_rank(X):
     assert not cp.value
 
 
+def test_comm_reduce_single_rank(X):
+    """comm_reduce__T folds a host array with op (src/comm.upc:961-984); n=0
+    returns the identity of gs_defs.h:45-52."""
+    import numpy as np
+    L = ctypes.CDLL(X.LIB_PATH)
+    cp = ctypes.c_void_p()
+    L.exags_comm_init()
+    L.exags_comm_world(ctypes.byref(cp))
+    cases = (("double", ctypes.c_double, np.float64), ("float", ctypes.c_float, np.float32),
+             ("int", ctypes.c_int, np.int32), ("long", ctypes.c_long, np.int64),
+             ("long_long", ctypes.c_longlong, np.int64))
+    for name, ct, dt in cases:
+        f = getattr(L, f"exags_comm_reduce__{name}")
+        f.restype = ct
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint]
+        v = np.array([3, -2, 5, 4], dtype=dt)
+        want = (v[0] + v[1] + v[2] + v[3], v[0] * v[1] * v[2] * v[3], v.min(), v.max())
+        for op in range(4):
+            assert f(cp, op, v.ctypes.data, 4) == want[op], (name, op)
+        assert f(cp, X.gs_add, None, 0) == 0 and f(cp, X.gs_mul, None, 0) == 1
+    L.exags_comm_free(ctypes.byref(cp))
+
+
 def test_compat_headers_compile(tmp_path):
     """A caller written against the reference's header names compiles."""
     src = tmp_path / "caller.c"
@@ -92,6 +115,8 @@ int caller(void) {
   id[0]=1; id[1]=1; id[2]=2; id[3]=0;
   gsh = gs_setup(id, 4, cp, 0, gs_pairwise, 0); free(id);
   gs(v, gs_double, gs_add, 0, gsh, &b);
+  { sint one = 1; slong two = 2; (void)comm_reduce_sint(cp, gs_max, &one, 1); (void)comm_reduce_slong(cp, gs_add, &two, 1);
+    (void)comm_reduce_double(cp, gs_add, v, 4); }
   gs_free(gsh); comm_free(&cp);
   return (int)cp->np;
 }''')
