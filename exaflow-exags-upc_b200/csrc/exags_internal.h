@@ -293,6 +293,43 @@ void xcu_csr_gather(void *stream, const struct xcu_csr *m, const struct xcu_fiel
 void xcu_csr_scatter(void *stream, const struct xcu_csr *m, const struct xcu_field *out,
                      int omode, const struct xcu_field *in, int imode, int xdom);
 
+/* ---- gs_setup on the device (setup_cuda.cu, setup_pipeline.h) ------------- */
+/* The label sort, group discovery and map construction of gs_setup as device
+   passes (replaces nonzero_ids / local_map / flagged_primaries_map,
+   src/gs.upc:83-112,329-370, and this library's own host builders in topo.c,
+   whose output it reproduces array for array).  All pointers below are device
+   pointers.                                                                  */
+struct xcu_topo {               /* struct xg_topo in HBM                       */
+  size_t n, nnz, ngrp;
+  u64 *id; u32 *idx; unsigned char *flag; u32 *gstart;
+  u32 *rowgrp;                  /* [nnz] group of each row                      */
+  int any_flag;
+};
+struct xcu_dmap {               /* struct xg_hmap in HBM                       */
+  u32 ng, ni;
+  u32 *off, *idx, *nunf;
+};
+struct xcu_dsell {              /* struct xg_sell in HBM                       */
+  u32 nblock, nwin;
+  size_t nidx;
+  unsigned char *mask, *fmask;
+  u32 *idx, *win_min, *win_max;
+  struct xcu_dmap rest;
+};
+/* id: host or device array of n labels, idbytes 4 (int) or 8 (long long)     */
+void xcu_setup_topo(const void *id, int idbytes, size_t n, struct xcu_topo *t);
+void xcu_setup_topo_free(struct xcu_topo *t);
+void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht);
+/* hall: every group with >= 2 members; fp: all flagged primaries; fs: flagged
+   primaries that head no multi-member group; sectors: distinct 32-byte sectors
+   of a double field that hold a member of hall                               */
+void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
+                     u32 **fs, u32 *nfs, u64 *sectors);
+void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s);
+void xcu_dmap_free(struct xcu_dmap *m);
+void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h);
+void xcu_note_launches(unsigned long long k);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@
 
 static unsigned long long g_launches = 0;
 #define LAUNCHED() do { ++g_launches; CU(cudaGetLastError()); } while (0)
+extern "C" void xcu_note_launches(unsigned long long k) { g_launches += k; }
 
 // ---------------------------------------------------------------------------
 // monoid definitions (src/gs_defs.h:33-52)

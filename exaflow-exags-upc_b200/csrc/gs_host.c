@@ -34,6 +34,11 @@ struct gs_data {
   u32 *hfp; u32 nfp;          /* all flagged primaries (src/gs.upc:359-370) */
   struct xg_plan plan;        /* np > 1 */
   u64 sectors_f64;            /* distinct 32-byte sectors of a double field touched */
+  /* device-built handles (np == 1): hall / hfp stay in HBM and are fetched
+     into the host copies above only when the introspection calls ask        */
+  int dev_built;
+  struct xcu_dmap d_hall;
+  u32 *d_hfp;
   /* device */
   struct dev_csr d_int;       /* interior groups (all groups when np == 1): CSR form,
                                  or only the long-group residue when d_sell is used */
@@ -851,7 +856,91 @@ static double time_exchange(struct gs_data *g, int method)
   return t;
 }
 
-static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, int unique,
+/* gs_setup's label sort and group discovery run on the device whenever there
+   is one (EXAGS_SETUP=host keeps the host builders of topo.c; both produce the
+   same arrays).  With one rank the maps are built there too and never visit
+   the host; with several ranks the topology comes back for the shared-label
+   discovery and the exchange plan, which are host code.                      */
+static int setup_on_device(const struct gs_data *g)
+{
+  const char *e = getenv("EXAGS_SETUP");
+  return g->on_device && !(e && strcmp(e, "host") == 0);
+}
+
+static i64 label_at(const void *id, int idbytes, size_t i)
+{
+  return idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+}
+
+static void topo_any(struct gs_data *g, struct xg_topo *topo, const void *id, int idbytes, u32 n)
+{
+  if (setup_on_device(g)) {
+    struct xcu_topo dt;
+    xcu_setup_topo(id, idbytes, n, &dt);
+    xcu_setup_topo_to_host(&dt, topo);
+    xcu_setup_topo_free(&dt);
+  } else if (idbytes == 8) xg_topo_build(topo, (const i64 *)id, n);
+  else {
+    i64 *wide = xnew(i64, n ? n : 1);
+    for (u32 i = 0; i < n; ++i) wide[i] = ((const int *)id)[i];
+    xg_topo_build(topo, wide, n);
+    free(wide);
+  }
+}
+
+/* one rank, device present: maps built in HBM (setup_cuda.cu)               */
+static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32 n, int prof)
+{
+  double tp[6]; int ntp = 0;
+#define TICK() do { if (prof) { xcu_device_sync(); exags_comm_time(&tp[ntp++]); } } while (0)
+  struct xcu_topo dt;
+  struct xcu_dsell ds;
+  u32 *d_fs = 0;
+  TICK();
+  xcu_setup_topo(id, idbytes, n, &dt);
+  TICK();
+  xcu_setup_local(&dt, &g->d_hall, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
+  xcu_setup_topo_free(&dt);
+  TICK();
+  xcu_setup_sell(&g->d_hall, &ds);
+  TICK();
+  g->dev_built = 1;
+  g->d_fs = d_fs;
+  g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;      /* counts now, arrays on demand */
+  g->d_sell.nblock = ds.nblock;
+  g->d_sell.mask = ds.mask; g->d_sell.idx = ds.idx; g->d_sell.fmask = ds.fmask;
+  g->d_sell_mem[0] = ds.mask; g->d_sell_mem[1] = ds.idx; g->d_sell_mem[2] = ds.fmask;
+  g->sell_idx_entries = ds.nidx;
+  g->d_int.c.ng = ds.rest.ng; g->d_int.c.ni = ds.rest.ni;
+  g->d_int.off = ds.rest.off; g->d_int.idx = ds.rest.idx; g->d_int.nunf = ds.rest.nunf;
+  g->d_int.c.off = ds.rest.off; g->d_int.c.idx = ds.rest.idx; g->d_int.c.nunf = ds.rest.nunf;
+  if (ds.nwin && !ds.rest.ng && !g->nfs) {
+    /* what the pipelined host-pointer path needs to schedule windows by chunk */
+    g->nwin = ds.nwin;
+    g->win_min = xnew(u32, ds.nwin); g->win_max = xnew(u32, ds.nwin);
+    xcu_d2h(g->win_min, ds.win_min, (size_t)ds.nwin * sizeof(u32), 0);
+    xcu_d2h(g->win_max, ds.win_max, (size_t)ds.nwin * sizeof(u32), 0);
+    xcu_device_sync();
+  }
+  xcu_free(ds.win_min); xcu_free(ds.win_max);
+  g->handle_bytes = sizeof *g + ((size_t)g->d_hall.ng + 1 + g->d_hall.ni + g->nfs + 1) * sizeof(u32);
+  TICK();
+  if (prof)
+    printf("gs_setup profile (device, n=%u): label sort+groups %.3f s, local map+sectors %.3f s, "
+           "sliced layout %.3f s, finish %.3f s\n", n, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
+#undef TICK
+}
+
+/* host copies of a device-built handle's group map, for the introspection calls */
+static void fetch_host_maps(struct gs_data *g)
+{
+  if (!g->dev_built || g->hall.off) return;
+  xcu_dmap_to_host(&g->d_hall, &g->hall);
+  g->hfp = xnew(u32, g->nfp ? g->nfp : 1);
+  if (g->nfp) { xcu_d2h(g->hfp, g->d_hfp, (size_t)g->nfp * sizeof(u32), 0); xcu_device_sync(); }
+}
+
+static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const comm_ptr comm, int unique,
                                   int method, int verbose)
 {
   if (!comm) xfail("gs_setup: null communicator");
@@ -868,32 +957,57 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
             "(set EXAGS_HOST_SETUP_ONLY=1 only to inspect the host-side maps)");
   }
   const int np = comm->np;
-  const i64 *id = id_in;
+  /* labels may live in HBM already (extension); the passes that read them on
+     the host get a staged copy */
+  void *id_staged = 0;
+  if (g->on_device && n && xcu_is_device_ptr(id_in) && (unique || !setup_on_device(g))) {
+    id_staged = xmalloc_((size_t)n * (size_t)idbytes, __FILE__, __LINE__);
+    xcu_d2h(id_staged, id_in, (size_t)n * (size_t)idbytes, 0);
+    xcu_device_sync();
+    id_in = id_staged;
+  }
+  const void *id = id_in;
   i64 *id_own = 0;
   struct xg_topo topo;
   struct xg_shared sh;
   const char *prof_env = getenv("EXAGS_SETUP_PROFILE");
   const int prof = prof_env && atoi(prof_env) && comm->id == 0;
+  const char *lay = getenv("EXAGS_LAYOUT");
+  const int dev_maps = np == 1 && setup_on_device(g) && !(lay && strcmp(lay, "csr") == 0);
   double tp[8]; int ntp = 0;
 #define TICK() do { if (prof) exags_comm_time(&tp[ntp++]); } while (0)
   TICK();
-  xg_topo_build(&topo, id, n);
-  xg_shared_discover(&sh, &topo, w);
   if (unique) {
     /* same outcome as gs_unique followed by a plain setup (src/gs.h) */
+    topo_any(g, &topo, id, idbytes, n);
+    xg_shared_discover(&sh, &topo, w);
     unsigned char *nf = xnew(unsigned char, n ? n : 1);
     xg_unique_flags(nf, n, &topo, &sh, comm->id);
     id_own = xnew(i64, n ? n : 1);
     for (u32 i = 0; i < n; ++i) {
-      i64 a = id_in[i] < 0 ? -id_in[i] : id_in[i];
+      i64 v = label_at(id_in, idbytes, i);
+      i64 a = v < 0 ? -v : v;
       id_own[i] = nf[i] ? -a : a;
     }
     free(nf);
     xg_topo_free(&topo); xg_shared_free(&sh);
-    id = id_own;
-    xg_topo_build(&topo, id, n);
-    xg_shared_discover(&sh, &topo, w);
+    id = id_own; idbytes = 8;
   }
+  if (dev_maps) {
+    setup_device_np1(g, id, idbytes, n, prof);
+    free(id_own); free(id_staged);
+    g->method = method == gs_all_reduce ? gs_all_reduce : gs_pairwise;
+    if (verbose && comm->id == 0) {
+      printf("gs_setup: %ld unique labels shared\n", 0L);
+      printf("   handle bytes (avg, min, max): %g %u %u\n", (double)g->handle_bytes,
+             (unsigned)g->handle_bytes, (unsigned)g->handle_bytes);
+      printf("   buffer bytes (avg, min, max): %g %u %u\n", 0.0, 0u, 0u);
+    }
+    fflush(stdout);
+    return g;
+  }
+  topo_any(g, &topo, id, idbytes, n);
+  xg_shared_discover(&sh, &topo, w);
 
   TICK();
   xg_topo_local_map(&topo, 1, &g->hall);
@@ -919,7 +1033,7 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
     (void)xg_world_nccl(w);       /* the push transport needs NCCL only for the all-reduce method */
   xg_shared_free(&sh);
   xg_topo_free(&topo);
-  free(id_own);
+  free(id_own); free(id_staged);
 
   if (verbose && comm->id == 0)
     printf("gs_setup: %ld unique labels shared\n", (long)g->plan.total_shared);
@@ -964,17 +1078,13 @@ static struct gs_data *setup_core(const i64 *id_in, u32 n, const comm_ptr comm, 
 struct gs_data *gslib_gs_setup(const long long *id, exags_uint n, const comm_ptr comm,
                                int unique, int method, int verbose)
 {
-  return setup_core((const i64 *)id, n, comm, unique, method, verbose);
+  return setup_core(id, 8, n, comm, unique, method, verbose);
 }
 
 struct gs_data *exags_gs_setup(const int *id, exags_uint n, const comm_ptr comm, int unique,
                                gs_method method, int verbose)
 {
-  i64 *wide = xnew(i64, n ? n : 1);
-  for (exags_uint i = 0; i < n; ++i) wide[i] = id[i];
-  struct gs_data *g = setup_core(wide, n, comm, unique, (int)method, verbose);
-  free(wide);
-  return g;
+  return setup_core(id, 4, n, comm, unique, (int)method, verbose);
 }
 
 void exags_gs_free(struct gs_data *g)
@@ -989,6 +1099,7 @@ void exags_gs_free(struct gs_data *g)
     for (int m = 0; m < 20; ++m) xcu_free(g->d_bnd_mem[m]);
     xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);
+    if (g->dev_built) { xcu_dmap_free(&g->d_hall); xcu_free(g->d_hfp); }
   }
   xg_hmap_free(&g->hall);
   free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);
@@ -1004,7 +1115,9 @@ static void unique_core(i64 *id, u32 n, const comm_ptr comm)
   if (!comm) xfail("gs_unique: null communicator");
   struct xg_world *w = (struct xg_world *)comm->priv;
   struct xg_topo topo; struct xg_shared sh;
-  xg_topo_build(&topo, id, n);
+  struct gs_data probe; memset(&probe, 0, sizeof probe);
+  probe.on_device = xg_world_has_cuda(w);
+  topo_any(&probe, &topo, id, 8, n);
   xg_shared_discover(&sh, &topo, w);
   unsigned char *nf = xnew(unsigned char, n ? n : 1);
   xg_unique_flags(nf, n, &topo, &sh, comm->id);
@@ -1043,6 +1156,7 @@ void exags_gs_info(const struct gs_data *g, unsigned long long what[16])
 size_t exags_gs_dump_map(const struct gs_data *g, int which, exags_uint *out, size_t cap)
 {
   size_t o = 0;
+  fetch_host_maps((struct gs_data *)g);
 #define PUT(v) do { if (o < cap) out[o] = (v); ++o; } while (0)
   if (which == 0 || which == 1) {
     const struct xg_hmap *m = &g->hall;

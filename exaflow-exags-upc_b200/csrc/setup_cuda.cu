@@ -1,0 +1,249 @@
+// setup_cuda.cu -- gs_setup's label sort, group discovery and map construction
+// on the device: the CUDA backend of setup_pipeline.h plus the thin C ABI the
+// host C code calls it through.
+//
+// The passes themselves (setup_pipeline.h) are this library's own kernels, one
+// item per thread; the stable radix sort of the (label, index) rows, the
+// prefix sums and the two reductions are CUB device primitives from the CUDA
+// toolkit -- library code, used here as gs_setup's sort (the reference's own is
+// sort_imp.h's radix/merge hybrid, src/sort_imp.h:446-509), not on the per-call
+// path.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "setup_pipeline.h"
+
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      exags_fail(1, __FILE__, __LINE__, "CUDA error: %s (%s)",                \
+                 cudaGetErrorString(e_), #call);                              \
+  } while (0)
+
+template <class F>
+__global__ void __launch_bounds__(256) k_setup_for_each(size_t n, F f)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+namespace {
+
+struct CudaBackend {
+  cudaStream_t st = 0;
+  void *tmp = nullptr;            // CUB scratch, grow-only
+  size_t tmp_bytes = 0;
+  u64 *res = nullptr;             // reduction result (device) + pinned mirror
+  u64 *res_h = nullptr;
+  unsigned long long launches = 0;
+  int sms = 148;
+
+  CudaBackend()
+  {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaMalloc(&res, 64));
+    CU(cudaMallocHost(&res_h, 64));
+  }
+  ~CudaBackend()
+  {
+    cudaStreamSynchronize(st);
+    cudaFree(tmp); cudaFree(res); cudaFreeHost(res_h);
+    xcu_note_launches(launches);
+  }
+  CudaBackend(const CudaBackend &) = delete;
+  CudaBackend &operator=(const CudaBackend &) = delete;
+
+  template <class T> T *alloc(size_t count)
+  {
+    void *p = nullptr;
+    CU(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    return (T *)p;
+  }
+  void release(void *p)
+  {
+    if (!p) return;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(p));
+  }
+  void zero(void *p, size_t bytes) { CU(cudaMemsetAsync(p, 0, bytes, st)); }
+  void fill_ff(void *p, size_t bytes) { CU(cudaMemsetAsync(p, 0xFF, bytes, st)); }
+
+  template <class F> void for_each(size_t n, F f)
+  {
+    if (!n) return;
+    const unsigned threads = 256;
+    size_t blocks = (n + threads - 1) / threads;
+    const size_t cap = (size_t)sms * 32;        // grid-stride beyond 32 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    k_setup_for_each<<<(unsigned)blocks, threads, 0, st>>>(n, f);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  void need_tmp(size_t bytes)
+  {
+    if (bytes <= tmp_bytes) return;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(tmp));
+    CU(cudaMalloc(&tmp, bytes));
+    tmp_bytes = bytes;
+  }
+  void sort_pairs(u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, size_t n, unsigned bits)
+  {
+    if (n < 2) return;
+    cub::DoubleBuffer<u64> dk(k, k2);
+    cub::DoubleBuffer<u32> dv(v, v2);
+    size_t bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (unsigned long long)n, 0, (int)bits, st));
+    need_tmp(bytes);
+    CU(cub::DeviceRadixSort::SortPairs(tmp, bytes, dk, dv, (unsigned long long)n, 0, (int)bits, st));
+    ++launches;
+    if (dk.Current() != k) { u64 *t = k; k = k2; k2 = t; }
+    if (dv.Current() != v) { u32 *t = v; v = v2; v2 = t; }
+  }
+  void scan(u32 *p, size_t n)
+  {
+    if (!n) return;
+    size_t bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, p, p, (unsigned long long)n, st));
+    need_tmp(bytes);
+    CU(cub::DeviceScan::ExclusiveSum(tmp, bytes, p, p, (unsigned long long)n, st));
+    ++launches;
+  }
+  u64 max_u64(const u64 *p, size_t n)
+  {
+    size_t bytes = 0;
+    CU(cub::DeviceReduce::Max(nullptr, bytes, p, res, (unsigned long long)n, st));
+    need_tmp(bytes);
+    CU(cub::DeviceReduce::Max(tmp, bytes, p, res, (unsigned long long)n, st));
+    ++launches;
+    CU(cudaMemcpyAsync(res_h, res, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return res_h[0];
+  }
+  u64 sum_u32(const u32 *p, size_t n)
+  {
+    size_t bytes = 0;
+    CU(cub::DeviceReduce::Sum(nullptr, bytes, p, res, (unsigned long long)n, st));
+    need_tmp(bytes);
+    CU(cub::DeviceReduce::Sum(tmp, bytes, p, res, (unsigned long long)n, st));
+    ++launches;
+    CU(cudaMemcpyAsync(res_h, res, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return res_h[0];
+  }
+  u32 get(const u32 *p)
+  {
+    CU(cudaMemcpyAsync(res_h, p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return *(const u32 *)res_h;
+  }
+};
+
+void check(int rc, const char *what)
+{
+  switch (rc) {
+    case xgsetup::OK: return;
+    case xgsetup::ERR_ID_TOO_LARGE: exags_fail(1, __FILE__, __LINE__, "gs_setup: |id| is too large (%s)", what); break;
+    case xgsetup::ERR_MAP_TOO_LARGE: exags_fail(1, __FILE__, __LINE__, "gs_setup: local map too large (%s)", what); break;
+    case xgsetup::ERR_SELL_TOO_LARGE: exags_fail(1, __FILE__, __LINE__, "gs_setup: map too large for the sliced layout (%s)", what); break;
+    default: exags_fail(1, __FILE__, __LINE__, "gs_setup: internal error packing the sliced layout (%s)", what);
+  }
+}
+
+bool is_device_ptr(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+void xcu_setup_topo(const void *id, int idbytes, size_t n, struct xcu_topo *t)
+{
+  if (n >= (size_t)XG_NONE)
+    exags_fail(1, __FILE__, __LINE__, "gs_setup: local size %lu does not fit the 32-bit index type", (unsigned long)n);
+  CudaBackend be;
+  const void *d_id = id;
+  void *own = nullptr;
+  if (n && !is_device_ptr(id)) {
+    CU(cudaMalloc(&own, n * (size_t)idbytes));
+    CU(cudaMemcpyAsync(own, id, n * (size_t)idbytes, cudaMemcpyHostToDevice, be.st));
+    d_id = own;
+  }
+  u64 maxabs = 0;
+  const int rc = xgsetup::topo_build(be, d_id, idbytes, n, t, &maxabs);
+  if (own) be.release(own);
+  if (rc == xgsetup::ERR_ID_TOO_LARGE)
+    exags_fail(1, __FILE__, __LINE__, "gs_setup: |id| = %llu is too large", (unsigned long long)maxabs);
+  check(rc, "topology");
+  CU(cudaStreamSynchronize(be.st));
+}
+
+void xcu_setup_topo_free(struct xcu_topo *t)
+{
+  CudaBackend be;
+  xgsetup::topo_release(be, t);
+}
+
+void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht)
+{
+  memset(ht, 0, sizeof *ht);
+  const size_t nnz = dt->nnz, ngrp = dt->ngrp;
+  ht->nnz = nnz; ht->ngrp = ngrp;
+  ht->id = xnew(u64, ngrp ? ngrp : 1);
+  ht->idx = xnew(u32, nnz ? nnz : 1);
+  ht->flag = xnew(unsigned char, nnz ? nnz : 1);
+  ht->gstart = xnew(u32, ngrp + 1);
+  if (ngrp) CU(cudaMemcpy(ht->id, dt->id, ngrp * sizeof(u64), cudaMemcpyDeviceToHost));
+  if (nnz) CU(cudaMemcpy(ht->idx, dt->idx, nnz * sizeof(u32), cudaMemcpyDeviceToHost));
+  if (nnz) CU(cudaMemcpy(ht->flag, dt->flag, nnz, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ht->gstart, dt->gstart, (ngrp + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
+}
+
+void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
+                     u32 **fs, u32 *nfs, u64 *sectors)
+{
+  CudaBackend be;
+  check(xgsetup::local_maps(be, t, hall, fp, nfp, fs, nfs, sectors), "local maps");
+  CU(cudaStreamSynchronize(be.st));
+}
+
+void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
+{
+  CudaBackend be;
+  check(xgsetup::sell_build(be, m, s), "sliced layout");
+  CU(cudaStreamSynchronize(be.st));
+}
+
+void xcu_dmap_free(struct xcu_dmap *m)
+{
+  CudaBackend be;
+  xgsetup::dmap_release(be, m);
+}
+
+void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h)
+{
+  memset(h, 0, sizeof *h);
+  h->ng = m->ng; h->ni = m->ni;
+  h->off = xnew(u32, (size_t)m->ng + 1);
+  h->idx = xnew(u32, m->ni ? m->ni : 1);
+  if (m->off) CU(cudaMemcpy(h->off, m->off, ((size_t)m->ng + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
+  else h->off[0] = 0;
+  if (m->ni) CU(cudaMemcpy(h->idx, m->idx, (size_t)m->ni * sizeof(u32), cudaMemcpyDeviceToHost));
+  if (m->nunf) {
+    h->nunf = xnew(u32, m->ng ? m->ng : 1);
+    if (m->ng) CU(cudaMemcpy(h->nunf, m->nunf, (size_t)m->ng * sizeof(u32), cudaMemcpyDeviceToHost));
+  }
+}
+
+}  // extern "C"

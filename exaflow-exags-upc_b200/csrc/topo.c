@@ -247,7 +247,8 @@ void xg_sell_free(struct xg_sell *s)
   memset(s, 0, sizeof *s);
 }
 
-static inline u32 sell_width(u32 size) { return size <= 2 ? 2u : size <= 4 ? 4u : 8u; }
+#include "sell_window.h"
+#define sell_width xg_sell_width
 
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
 {
@@ -290,19 +291,19 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
     }
     ++nwin;
   }
-  size_t *wfirst = xnew(size_t, nwin + 1);
+  u32 *wfirst = xnew(u32, nwin + 1);
   {
     size_t w = 0;
     for (size_t k = 0; k < nshort;) {
       u32 used = 0;
-      wfirst[w++] = k;
+      wfirst[w++] = (u32)k;
       while (k < nshort) {
         u32 wd = sell_width(m->off[sg[k] + 1] - m->off[sg[k]]);
         if (used + wd > WSLOTS) break;
         used += wd; ++k;
       }
     }
-    wfirst[nwin] = nshort;
+    wfirst[nwin] = (u32)nshort;
   }
   if ((nwin * XG_SELL_WB) >> 23) xfail("gs_setup: map too large for the sliced layout");
   s->nblock = (u32)(nwin * XG_SELL_WB);
@@ -313,56 +314,13 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   s->mask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   if (m->nunf) s->fmask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
+  int bad = 0;
 #ifdef _OPENMP
-#pragma omp parallel num_threads(xg_setup_threads())
+#pragma omp parallel for schedule(dynamic, 64) num_threads(xg_setup_threads()) reduction(| : bad)
 #endif
-  {
-    unsigned char fill[XG_SELL_WB * 32];
-#ifdef _OPENMP
-#pragma omp for schedule(dynamic, 64)
-#endif
-    for (size_t w = 0; w < nwin; ++w) {
-      u32 *base = s->idx + w * WSLOTS;
-      unsigned char *mk = s->mask + w * XG_SELL_WB * 32;
-      for (u32 z = 0; z < WSLOTS; ++z) base[z] = XG_NONE;
-      memset(fill, 0, sizeof fill);
-      {
-        u32 lo = XG_NONE, hi = 0;
-        for (size_t k = wfirst[w]; k < wfirst[w + 1]; ++k)
-          for (u32 q = m->off[sg[k]]; q < m->off[sg[k] + 1]; ++q) {
-            if (m->idx[q] < lo) lo = m->idx[q];
-            if (m->idx[q] > hi) hi = m->idx[q];
-          }
-        s->win_min[w] = lo; s->win_max[w] = hi;
-      }
-      /* descending width, stable in primary order; rows of equal width are
-         dealt lane after lane, block after block */
-      for (u32 wd = 8; wd >= 2; wd >>= 1) {
-        u32 pos = 0;                                /* lane cursor over the window */
-        for (size_t k = wfirst[w]; k < wfirst[w + 1]; ++k) {
-          u32 g = sg[k], a = m->off[g], sz = m->off[g + 1] - a;
-          if (sell_width(sz) != wd) continue;
-          /* next lane (block-major, then lane) with room; fills are multiples
-             of wd here, and lanes before the cursor are at least as full */
-          u32 tries = 0;
-          while (fill[pos] + wd > 8) {
-            pos = (pos + 1) % (XG_SELL_WB * 32);
-            if (++tries > XG_SELL_WB * 32) xfail("gs_setup: internal error packing the sliced layout");
-          }
-          u32 *slot = base + (size_t)pos * 8 + fill[pos];
-          for (u32 q = 0; q < sz; ++q) slot[q] = m->idx[a + q];
-          mk[pos] |= (unsigned char)(1u << fill[pos]);
-          if (s->fmask) {                            /* members [nunf, sz) are flagged */
-            u32 unf = m->nunf[g];
-            s->fmask[w * XG_SELL_WB * 32 + pos] |= (unsigned char)((((1u << sz) - 1u) & ~((1u << unf) - 1u)) << fill[pos]);
-          }
-          fill[pos] = (unsigned char)(fill[pos] + wd);
-          /* row-major dealing: move on to the next lane; wrap to start a new
-             row of this width */
-          pos = (pos + 1) % (XG_SELL_WB * 32);
-        }
-      }
-    }
-  }
+  for (size_t w = 0; w < nwin; ++w)
+    bad |= xg_sell_fill_window(w, wfirst[w], wfirst[w + 1], sg, m->off, m->idx, m->nunf,
+                               s->idx, s->mask, s->fmask, s->win_min, s->win_max);
+  if (bad) xfail("gs_setup: internal error packing the sliced layout");
   free(wfirst); free(sg);
 }

@@ -175,17 +175,23 @@ def gs_setup(ids, comm=None, unique: int = 0, method: int = gs_pairwise, verbose
     """gs_setup(id, n, comm, unique, method, verbose) (src/gs.upc:1262-1269).
     int64 ids take the Nek flavour (gslib_, GLOBAL_LONG_LONG), int32 ids the
     default flavour (exags_)."""
-    ids = np.ascontiguousarray(ids)
     cp = comm if comm is not None else comm_world()
-    if ids.dtype == np.int64:
-        p = lib().gslib_gs_setup(ids.ctypes.data, ids.size, cp, unique, method, verbose)
-        wide = True
-    elif ids.dtype == np.int32:
-        p = lib().exags_gs_setup(ids.ctypes.data, ids.size, cp, unique, method, verbose)
-        wide = False
+    if hasattr(ids, "data_ptr"):          # torch tensor: labels already in HBM (extension)
+        if not ids.is_contiguous():
+            raise ValueError("ids must be contiguous")
+        size, itemsize = ids.numel(), ids.element_size()
+    else:
+        ids = np.ascontiguousarray(ids)
+        if ids.dtype not in (np.int64, np.int32):
+            raise TypeError("ids must be int32 or int64")
+        size, itemsize = ids.size, ids.dtype.itemsize
+    if itemsize == 8:
+        p = lib().gslib_gs_setup(_addr(ids), size, cp, unique, method, verbose)
+    elif itemsize == 4:
+        p = lib().exags_gs_setup(_addr(ids), size, cp, unique, method, verbose)
     else:
         raise TypeError("ids must be int32 or int64")
-    return GS(p, int(ids.size), wide)
+    return GS(p, int(size), itemsize == 8)
 
 
 def gs(u, dom: int, op: int, transpose: int, gsh: GS, buf=None) -> None:

@@ -1,0 +1,132 @@
+// setup_emul.cpp -- TEST CODE.  Instantiates the device gs_setup passes of
+// csrc/setup_pipeline.h with a sequential host backend and compares every
+// array they produce with the host builders of csrc/topo.c (xg_topo_build,
+// xg_topo_local_map, xg_topo_flagged_primaries, xg_sell_build).  This checks
+// the index logic of the passes on machines without a GPU; the CUDA backend
+// (kernel launch, CUB sort / scan / reduce) is exercised by the -m gpu tests.
+// Nothing in the library links or calls this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "setup_pipeline.h"
+
+namespace {
+struct HostBackend {
+  bool reverse = false;       // run for_each back to front: passes must not depend on item order
+  template <class T> T *alloc(size_t count) { return (T *)malloc((count ? count : 1) * sizeof(T)); }
+  void release(void *p) { free(p); }
+  void zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+  void fill_ff(void *p, size_t bytes) { memset(p, 0xFF, bytes); }
+  template <class F> void for_each(size_t n, F f)
+  {
+    if (reverse) for (size_t i = n; i-- > 0;) f(i);
+    else for (size_t i = 0; i < n; ++i) f(i);
+  }
+  void sort_pairs(u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, size_t n, unsigned bits)
+  {
+    const u64 m = bits >= 64 ? ~(u64)0 : (((u64)1 << bits) - 1);
+    std::vector<size_t> p(n);
+    std::iota(p.begin(), p.end(), (size_t)0);
+    std::stable_sort(p.begin(), p.end(), [&](size_t a, size_t b) { return (k[a] & m) < (k[b] & m); });
+    for (size_t i = 0; i < n; ++i) { k2[i] = k[p[i]]; v2[i] = v[p[i]]; }
+    std::swap(k, k2); std::swap(v, v2);     // result must be reachable through k / v
+  }
+  void scan(u32 *p, size_t n) { u32 run = 0; for (size_t i = 0; i < n; ++i) { u32 x = p[i]; p[i] = run; run += x; } }
+  u64 max_u64(const u64 *p, size_t n) { u64 m = 0; for (size_t i = 0; i < n; ++i) m = std::max(m, p[i]); return m; }
+  u64 sum_u32(const u32 *p, size_t n) { u64 s = 0; for (size_t i = 0; i < n; ++i) s += p[i]; return s; }
+  u32 get(const u32 *p) { return *p; }
+};
+
+template <class T> bool same(const T *a, const T *b, size_t n) { return n == 0 || memcmp(a, b, n * sizeof(T)) == 0; }
+
+u64 host_sectors(const xg_hmap *m)
+{
+  if (!m->ni) return 0;
+  u32 maxi = 0;
+  for (u32 k = 0; k < m->ni; ++k) maxi = std::max(maxi, m->idx[k]);
+  std::vector<unsigned char> mark(((size_t)maxi * 8) / 32 + 1, 0);
+  for (u32 k = 0; k < m->ni; ++k) mark[((size_t)m->idx[k] * 8) / 32] = 1;
+  u64 c = 0;
+  for (unsigned char x : mark) c += x;
+  return c;
+}
+
+int compare_sell(const xcu_dsell &d, const xg_sell &h)
+{
+  if (d.nblock != h.nblock || d.nwin != h.nwin || d.nidx != h.nidx) return 40;
+  if (h.nblock) {
+    if (!same(d.idx, h.idx, h.nidx)) return 41;
+    if (!same(d.mask, h.mask, (size_t)h.nblock * 32 + 1)) return 42;
+    if ((d.fmask != 0) != (h.fmask != 0)) return 43;
+    if (h.fmask && !same(d.fmask, h.fmask, (size_t)h.nblock * 32 + 1)) return 44;
+    if (!same(d.win_min, h.win_min, h.nwin) || !same(d.win_max, h.win_max, h.nwin)) return 45;
+  }
+  if (d.rest.ng != h.rest.ng || d.rest.ni != h.rest.ni) return 46;
+  if (h.rest.ng) {
+    if (!same(d.rest.off, h.rest.off, (size_t)h.rest.ng + 1) || !same(d.rest.idx, h.rest.idx, h.rest.ni)) return 47;
+    if ((d.rest.nunf != 0) != (h.rest.nunf != 0)) return 48;
+    if (h.rest.nunf && !same(d.rest.nunf, h.rest.nunf, h.rest.ng)) return 49;
+  }
+  return 0;
+}
+}  // namespace
+
+// Returns 0 when every array matches, else a stage code (10s topology, 20s
+// local map, 30s flagged lists / sectors, 40s sliced layout).
+extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int reverse)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht;
+  xg_topo_build(&ht, wide.data(), n);
+  xg_hmap hh;
+  xg_topo_local_map(&ht, 1, &hh);
+  u32 hnfp = 0, hnfs = 0;
+  u32 *hfp = xg_topo_flagged_primaries(&ht, 0, &hnfp), *hfs = xg_topo_flagged_primaries(&ht, 1, &hnfs);
+  xg_sell hs;
+  xg_sell_build(&hs, &hh);
+
+  HostBackend be;
+  be.reverse = reverse != 0;
+  xcu_topo dt;
+  u64 maxabs = 0;
+  int rc = xgsetup::topo_build(be, id, idbytes, n, &dt, &maxabs), out = 0;
+  xcu_dmap dh; memset(&dh, 0, sizeof dh);
+  xcu_dsell ds; memset(&ds, 0, sizeof ds);
+  u32 *dfp = 0, *dfs = 0, dnfp = 0, dnfs = 0;
+  u64 sectors = 0;
+  if (rc) { out = 10; goto done; }
+  if (dt.nnz != ht.nnz || dt.ngrp != ht.ngrp) { out = 11; goto done; }
+  if (!same(dt.id, ht.id, ht.ngrp)) { out = 12; goto done; }
+  if (!same(dt.idx, ht.idx, ht.nnz)) { out = 13; goto done; }
+  if (!same(dt.flag, ht.flag, ht.nnz)) { out = 14; goto done; }
+  if (!same(dt.gstart, ht.gstart, ht.ngrp + 1)) { out = 15; goto done; }
+  for (size_t g = 0; g < ht.ngrp; ++g)
+    for (u32 j = ht.gstart[g]; j < ht.gstart[g + 1]; ++j) if (dt.rowgrp[j] != g) { out = 16; goto done; }
+
+  rc = xgsetup::local_maps(be, &dt, &dh, &dfp, &dnfp, &dfs, &dnfs, &sectors);
+  if (rc) { out = 20; goto done; }
+  if (dh.ng != hh.ng || dh.ni != hh.ni) { out = 21; goto done; }
+  if (!same(dh.off, hh.off, (size_t)hh.ng + 1) || !same(dh.idx, hh.idx, hh.ni)) { out = 22; goto done; }
+  if ((dh.nunf != 0) != (hh.nunf != 0)) { out = 23; goto done; }
+  if (hh.nunf && !same(dh.nunf, hh.nunf, hh.ng)) { out = 24; goto done; }
+  if (dt.any_flag) {
+    if (dnfp != hnfp || !same(dfp, hfp, hnfp)) { out = 30; goto done; }
+    if (dnfs != hnfs || !same(dfs, hfs, hnfs)) { out = 31; goto done; }
+  } else if (hnfp || hnfs) { out = 32; goto done; }
+  if (sectors != host_sectors(&hh)) { out = 33; goto done; }
+
+  rc = xgsetup::sell_build(be, &dh, &ds);
+  if (rc) { out = 39; goto done; }
+  out = compare_sell(ds, hs);
+done:
+  xgsetup::sell_release(be, &ds);
+  xgsetup::dmap_release(be, &dh);
+  be.release(dfp); be.release(dfs);
+  xgsetup::topo_release(be, &dt);
+  xg_sell_free(&hs); xg_hmap_free(&hh); free(hfp); free(hfs); xg_topo_free(&ht);
+  return out;
+}

@@ -1,0 +1,94 @@
+"""Index logic of the device gs_setup passes (csrc/setup_pipeline.h), checked
+without a GPU: tests/c/setup_emul.cpp instantiates the same pass source with a
+sequential host backend and compares every array (topology rows, local map,
+flagged-primary lists, sector count, sliced-ELL layout) with the host builders
+of csrc/topo.c.  The CUDA backend itself is covered by the -m gpu tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from exags_b200 import semmesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "exaflow-exags-upc_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "c", "build")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(OUT, exist_ok=True)
+    objs = []
+    for c in ("topo.c", "sort.c", "base.c"):
+        o = os.path.join(OUT, c[:-2] + ".o")
+        subprocess.run(["gcc", "-O2", "-fPIC", "-fopenmp", "-std=gnu11", "-I", os.path.join(ROOT, "include"),
+                        "-c", os.path.join(CSRC, c), "-o", o], check=True)
+        objs.append(o)
+    so = os.path.join(OUT, "libsetup_emul.so")
+    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-fopenmp", "-I", CSRC,
+                    os.path.join(ROOT, "tests", "c", "setup_emul.cpp")] + objs + ["-o", so], check=True)
+    L = ctypes.CDLL(so)
+    L.setup_emul_compare.restype = ctypes.c_int
+    L.setup_emul_compare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
+
+    def run(ids, reverse=0):
+        ids = np.ascontiguousarray(ids)
+        assert ids.dtype in (np.int64, np.int32)
+        return L.setup_emul_compare(ids.ctypes.data, ids.dtype.itemsize, ids.size, reverse)
+    return run
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_labels(emul, seed):
+    ids = cases.random_ids(3000 + 211 * seed, 700, seed, long_group=40 if seed % 2 else 0)
+    assert emul(ids) == 0
+    assert emul(ids, reverse=1) == 0
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_labels_unflagged(emul, seed):
+    ids = cases.random_ids(5000, 900, 100 + seed, p_flag=0.0, long_group=17 if seed else 0)
+    assert emul(ids) == 0
+    assert emul(ids.astype(np.int32), reverse=1) == 0
+
+
+@pytest.mark.parametrize("ids", [np.zeros(0, np.int64), np.zeros(5, np.int64),
+                                 np.array([7], np.int64), np.array([-7], np.int64),
+                                 np.arange(1, 50, dtype=np.int64),
+                                 np.array([3, 3], np.int64), np.array([-3, 3, 0, -3], np.int64),
+                                 np.full(9, 5, np.int64), np.full(8, -5, np.int64)],
+                         ids=["empty", "allzero", "single", "singleflag", "nogroups", "pair", "flagpair",
+                              "nine", "eightflagged"])
+def test_degenerate(emul, ids):
+    assert emul(ids) == 0
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2, 3), (5, 4, 3, 4), (16, 16, 6, 7), (7, 5, 3, 9), (40, 3, 2, 1)])
+def test_sem_boxes(emul, dims):
+    """Several windows of the sliced layout (16x16x6 N=7 has ~380 of them)."""
+    ids = semmesh.box_ids(*dims)
+    assert emul(ids) == 0
+    assert emul(ids, reverse=1) == 0
+
+
+def test_window_boundaries(emul):
+    """Group sizes chosen so that windows end with unused slots (a 4- or 8-wide
+    group that does not fit the remaining 2 or 6 slots) and lanes are skipped."""
+    rng = np.random.default_rng(5)
+    sizes = rng.choice([2, 3, 5, 8, 2, 2, 7], size=6000)
+    labels = np.repeat(np.arange(1, sizes.size + 1), sizes)
+    ids = labels[rng.permutation(labels.size)].astype(np.int64)
+    assert emul(ids) == 0
+    # primaries in label order: whole windows of one width, then a mix
+    sizes = np.concatenate([np.full(1500, 2), np.full(700, 8), np.full(900, 4), rng.choice([2, 4, 8], 3000)])
+    ids = np.repeat(np.arange(1, sizes.size + 1), sizes).astype(np.int64)
+    assert emul(ids) == 0
+    assert emul(ids, reverse=1) == 0
+
+
+def test_large_labels(emul):
+    ids = np.array([2**61, 5, -(2**61), 2**40, 5, 2**40, 0, 1], np.int64)
+    assert emul(ids) == 0
