@@ -329,6 +329,8 @@ void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s);
 void xcu_dmap_free(struct xcu_dmap *m);
 void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h);
 void xcu_note_launches(unsigned long long k);
+void xcu_setup_begin(void);   /* brackets the device passes of one gs_setup */
+void xcu_setup_end(void);
 
 #ifdef __cplusplus
 }

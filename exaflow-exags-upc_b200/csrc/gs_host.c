@@ -876,9 +876,11 @@ static void topo_any(struct gs_data *g, struct xg_topo *topo, const void *id, in
 {
   if (setup_on_device(g)) {
     struct xcu_topo dt;
+    xcu_setup_begin();
     xcu_setup_topo(id, idbytes, n, &dt);
     xcu_setup_topo_to_host(&dt, topo);
     xcu_setup_topo_free(&dt);
+    xcu_setup_end();
   } else if (idbytes == 8) xg_topo_build(topo, (const i64 *)id, n);
   else {
     i64 *wide = xnew(i64, n ? n : 1);
@@ -897,6 +899,7 @@ static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32
   struct xcu_dsell ds;
   u32 *d_fs = 0;
   TICK();
+  xcu_setup_begin();
   xcu_setup_topo(id, idbytes, n, &dt);
   TICK();
   xcu_setup_local(&dt, &g->d_hall, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
@@ -923,6 +926,7 @@ static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32
     xcu_device_sync();
   }
   xcu_free(ds.win_min); xcu_free(ds.win_max);
+  xcu_setup_end();
   g->handle_bytes = sizeof *g + ((size_t)g->d_hall.ng + 1 + g->d_hall.ni + g->nfs + 1) * sizeof(u32);
   TICK();
   if (prof)

@@ -34,43 +34,64 @@ __global__ void __launch_bounds__(256) k_setup_for_each(size_t n, F f)
 
 namespace {
 
+// One backend per process, created on first use and never destroyed (its
+// members would outlive the CUDA context at exit).  Work arrays come from the
+// device's stream-ordered memory pool: between begin() and end() the pool
+// keeps what the passes free, so the ~40 arrays of one gs_setup reuse each
+// other's memory instead of going to the driver; end() hands everything that
+// is not part of the finished handle back.  Arrays that survive (the maps of
+// the handle) are ordinary allocations of the same pool and are released with
+// cudaFree like any other.
 struct CudaBackend {
   cudaStream_t st = 0;
-  void *tmp = nullptr;            // CUB scratch, grow-only
+  void *tmp = nullptr;            // CUB scratch, grow-only until end()
   size_t tmp_bytes = 0;
   u64 *res = nullptr;             // reduction result (device) + pinned mirror
   u64 *res_h = nullptr;
   unsigned long long launches = 0;
   int sms = 148;
+  int dev = -1;
+  int depth = 0;
+  cudaMemPool_t pool = nullptr;
 
-  CudaBackend()
+  void begin()
   {
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CU(cudaMalloc(&res, 64));
-    CU(cudaMallocHost(&res_h, 64));
+    if (depth++) return;
+    int d = 0;
+    CU(cudaGetDevice(&d));
+    if (d != dev) {
+      dev = d;
+      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+      res = nullptr;              // per-device; the few bytes of a previous device stay behind
+      if (!res_h) CU(cudaMallocHost(&res_h, 64));
+    }
+    if (!res) CU(cudaMalloc(&res, 64));
+    unsigned long long keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
-  ~CudaBackend()
+  void end()
   {
-    cudaStreamSynchronize(st);
-    cudaFree(tmp); cudaFree(res); cudaFreeHost(res_h);
+    if (--depth) return;
+    CU(cudaStreamSynchronize(st));
+    if (tmp) { CU(cudaFreeAsync(tmp, st)); tmp = nullptr; tmp_bytes = 0; }
+    CU(cudaStreamSynchronize(st));
+    unsigned long long keep = 0;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CU(cudaMemPoolTrimTo(pool, 0));
     xcu_note_launches(launches);
+    launches = 0;
   }
-  CudaBackend(const CudaBackend &) = delete;
-  CudaBackend &operator=(const CudaBackend &) = delete;
 
   template <class T> T *alloc(size_t count)
   {
     void *p = nullptr;
-    CU(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    CU(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st));
     return (T *)p;
   }
   void release(void *p)
   {
-    if (!p) return;
-    CU(cudaStreamSynchronize(st));
-    CU(cudaFree(p));
+    if (p) CU(cudaFreeAsync(p, st));
   }
   void zero(void *p, size_t bytes) { CU(cudaMemsetAsync(p, 0, bytes, st)); }
   void fill_ff(void *p, size_t bytes) { CU(cudaMemsetAsync(p, 0xFF, bytes, st)); }
@@ -89,9 +110,8 @@ struct CudaBackend {
   void need_tmp(size_t bytes)
   {
     if (bytes <= tmp_bytes) return;
-    CU(cudaStreamSynchronize(st));
-    CU(cudaFree(tmp));
-    CU(cudaMalloc(&tmp, bytes));
+    if (tmp) CU(cudaFreeAsync(tmp, st));
+    CU(cudaMallocAsync(&tmp, bytes, st));
     tmp_bytes = bytes;
   }
   void sort_pairs(u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, size_t n, unsigned bits)
@@ -146,6 +166,17 @@ struct CudaBackend {
   }
 };
 
+CudaBackend &backend()
+{
+  static CudaBackend *be = new CudaBackend;
+  return *be;
+}
+struct Scope {                    // begin()/end() around one C-ABI call (nests)
+  CudaBackend &be;
+  Scope() : be(backend()) { be.begin(); }
+  ~Scope() { be.end(); }
+};
+
 void check(int rc, const char *what)
 {
   switch (rc) {
@@ -172,11 +203,11 @@ void xcu_setup_topo(const void *id, int idbytes, size_t n, struct xcu_topo *t)
 {
   if (n >= (size_t)XG_NONE)
     exags_fail(1, __FILE__, __LINE__, "gs_setup: local size %lu does not fit the 32-bit index type", (unsigned long)n);
-  CudaBackend be;
+  Scope sc; CudaBackend &be = sc.be;
   const void *d_id = id;
   void *own = nullptr;
   if (n && !is_device_ptr(id)) {
-    CU(cudaMalloc(&own, n * (size_t)idbytes));
+    own = be.alloc<char>(n * (size_t)idbytes);
     CU(cudaMemcpyAsync(own, id, n * (size_t)idbytes, cudaMemcpyHostToDevice, be.st));
     d_id = own;
   }
@@ -191,7 +222,7 @@ void xcu_setup_topo(const void *id, int idbytes, size_t n, struct xcu_topo *t)
 
 void xcu_setup_topo_free(struct xcu_topo *t)
 {
-  CudaBackend be;
+  Scope sc; CudaBackend &be = sc.be;
   xgsetup::topo_release(be, t);
 }
 
@@ -213,23 +244,27 @@ void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht)
 void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
                      u32 **fs, u32 *nfs, u64 *sectors)
 {
-  CudaBackend be;
+  Scope sc; CudaBackend &be = sc.be;
   check(xgsetup::local_maps(be, t, hall, fp, nfp, fs, nfs, sectors), "local maps");
   CU(cudaStreamSynchronize(be.st));
 }
 
 void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
 {
-  CudaBackend be;
+  Scope sc; CudaBackend &be = sc.be;
   check(xgsetup::sell_build(be, m, s), "sliced layout");
   CU(cudaStreamSynchronize(be.st));
 }
 
 void xcu_dmap_free(struct xcu_dmap *m)
 {
-  CudaBackend be;
+  Scope sc; CudaBackend &be = sc.be;
   xgsetup::dmap_release(be, m);
 }
+
+/* brackets one gs_setup: the work arrays of all its passes share the pool    */
+void xcu_setup_begin(void) { backend().begin(); }
+void xcu_setup_end(void) { backend().end(); }
 
 void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h)
 {
