@@ -325,6 +325,13 @@ void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht);
    of a double field that hold a member of hall                               */
 void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
                      u32 **fs, u32 *nfs, u64 *sectors);
+/* several ranks: bgrp = the nb boundary groups named by the exchange plan
+   (host array, ascending).  in = interior groups with >= 2 members, bnd = every
+   boundary group (all members, unflagged counts), bnd2 = boundary groups with
+   >= 2 members (only for maps without flagged labels), fs excludes the boundary */
+void xcu_setup_split(const struct xcu_topo *t, const u32 *bgrp_host, u32 nb, struct xcu_dmap *hall,
+                     struct xcu_dmap *in, struct xcu_dmap *bnd, struct xcu_dmap *bnd2,
+                     u32 **fp, u32 *nfp, u32 **fs, u32 *nfs, u64 *sectors);
 void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s);
 void xcu_dmap_free(struct xcu_dmap *m);
 void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h);

@@ -644,6 +644,39 @@ void gslib_gs_many(void *const *u, unsigned vn, int dom, int op, unsigned t, str
 /* ------------------------------------------------------------------ */
 /*  setup                                                              */
 /* ------------------------------------------------------------------ */
+/* the exchange plan's per-boundary-primary tables, into d_bnd_mem[m...]      */
+static int upload_boundary_plan(struct gs_data *g, int m)
+{
+  const struct xg_plan *pl = &g->plan;
+  struct xcu_bnd *d = &g->d_bnd;
+  const u32 nb = pl->nb;
+#define UP(dst, src, cnt) do { g->d_bnd_mem[m] = upload((src), (size_t)(cnt) * sizeof(*(src))); (dst) = g->d_bnd_mem[m]; ++m; } while (0)
+  for (int dd = 0; dd < 2; ++dd) {
+    UP(d->soff[dd], pl->soff[dd], nb + 1);
+    UP(d->slot[dd], pl->slot[dd], pl->total[dd] ? pl->total[dd] : 1);
+  }
+  UP(d->ord, pl->ord, nb);
+  UP(d->pflag, pl->pflag, nb);
+  for (int dd = 0; dd < 2; ++dd) UP(g->d_snb[dd], pl->snb[dd], pl->total[dd] ? pl->total[dd] : 1);
+#undef UP
+  return m;
+}
+
+/* the local primary behind every send slot, in slot order (symmetric maps) */
+static int upload_send_primaries(struct gs_data *g, int m)
+{
+  const struct xg_plan *pl = &g->plan;
+  for (int dd = 0; dd < 2; ++dd) {
+    u32 *sp = xnew(u32, pl->total[dd] ? pl->total[dd] : 1);
+    for (u32 b = 0; b < pl->nb; ++b)
+      for (u32 q = pl->soff[dd][b]; q < pl->soff[dd][b + 1]; ++q) sp[pl->slot[dd][q]] = pl->bprim[b];
+    g->d_bnd_mem[m] = upload(sp, (size_t)(pl->total[dd] ? pl->total[dd] : 1) * sizeof(u32));
+    g->d_sprim[dd] = (const u32 *)g->d_bnd_mem[m]; ++m;
+    free(sp);
+  }
+  return m;
+}
+
 static void split_groups(struct gs_data *g, const struct xg_topo *t)
 {
   /* interior CSR = groups (>= 2 members) whose primary is not a boundary
@@ -753,13 +786,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
       UP(d->goff, bgoff, nb + 1);
       UP(d->gidx, bgidx, bni ? bni : 1);
       UP(d->nunf, bnunf, nb);
-      for (int dd = 0; dd < 2; ++dd) {
-        UP(d->soff[dd], pl->soff[dd], nb + 1);
-        UP(d->slot[dd], pl->slot[dd], pl->total[dd] ? pl->total[dd] : 1);
-      }
-      UP(d->ord, pl->ord, nb);
-      UP(d->pflag, pl->pflag, nb);
-      for (int dd = 0; dd < 2; ++dd) UP(g->d_snb[dd], pl->snb[dd], pl->total[dd] ? pl->total[dd] : 1);
+      m = upload_boundary_plan(g, m);
       const char *bf = getenv("EXAGS_BND_FAST");
       if (!any_flag && !(bf && atoi(bf) == 0)) {
         /* boundary groups with >= 2 local members, sliced like the interior */
@@ -784,13 +811,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
           }
         }
         xg_sell_free(&bs); xg_hmap_free(&bh);
-        for (int dd = 0; dd < 2; ++dd) {
-          u32 *sp = xnew(u32, pl->total[dd] ? pl->total[dd] : 1);
-          for (u32 b = 0; b < nb; ++b)
-            for (u32 q = pl->soff[dd][b]; q < pl->soff[dd][b + 1]; ++q) sp[pl->slot[dd][q]] = pl->bprim[b];
-          UP(g->d_sprim[dd], sp, pl->total[dd] ? pl->total[dd] : 1);
-          free(sp);
-        }
+        m = upload_send_primaries(g, m);
         g->bnd_fast = 1;
       }
 #undef UP
@@ -890,26 +911,12 @@ static void topo_any(struct gs_data *g, struct xg_topo *topo, const void *id, in
   }
 }
 
-/* one rank, device present: maps built in HBM (setup_cuda.cu)               */
-static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32 n, int prof)
+/* the sliced layout of the interior map `in`, as the handle's d_sell / d_int,
+   plus what the pipelined host-pointer path keeps on the host               */
+static void adopt_interior(struct gs_data *g, const struct xcu_dmap *in, const struct xcu_dmap *bnd)
 {
-  double tp[6]; int ntp = 0;
-#define TICK() do { if (prof) { xcu_device_sync(); exags_comm_time(&tp[ntp++]); } } while (0)
-  struct xcu_topo dt;
   struct xcu_dsell ds;
-  u32 *d_fs = 0;
-  TICK();
-  xcu_setup_begin();
-  xcu_setup_topo(id, idbytes, n, &dt);
-  TICK();
-  xcu_setup_local(&dt, &g->d_hall, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
-  xcu_setup_topo_free(&dt);
-  TICK();
-  xcu_setup_sell(&g->d_hall, &ds);
-  TICK();
-  g->dev_built = 1;
-  g->d_fs = d_fs;
-  g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;      /* counts now, arrays on demand */
+  xcu_setup_sell(in, &ds);
   g->d_sell.nblock = ds.nblock;
   g->d_sell.mask = ds.mask; g->d_sell.idx = ds.idx; g->d_sell.fmask = ds.fmask;
   g->d_sell_mem[0] = ds.mask; g->d_sell_mem[1] = ds.idx; g->d_sell_mem[2] = ds.fmask;
@@ -923,9 +930,36 @@ static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32
     g->win_min = xnew(u32, ds.nwin); g->win_max = xnew(u32, ds.nwin);
     xcu_d2h(g->win_min, ds.win_min, (size_t)ds.nwin * sizeof(u32), 0);
     xcu_d2h(g->win_max, ds.win_max, (size_t)ds.nwin * sizeof(u32), 0);
+    if (bnd && bnd->ng && bnd->ni) {
+      g->h_bidx = xnew(u32, bnd->ni); g->h_nbidx = bnd->ni;
+      xcu_d2h(g->h_bidx, bnd->idx, (size_t)bnd->ni * sizeof(u32), 0);
+    }
     xcu_device_sync();
   }
   xcu_free(ds.win_min); xcu_free(ds.win_max);
+}
+
+/* one rank, device present: maps built in HBM (setup_cuda.cu)               */
+static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32 n, int prof)
+{
+  double tp[6]; int ntp = 0;
+#define TICK() do { if (prof) { xcu_device_sync(); exags_comm_time(&tp[ntp++]); } } while (0)
+  struct xcu_topo dt;
+  u32 *d_fs = 0;
+  TICK();
+  xcu_setup_begin();
+  xcu_setup_topo(id, idbytes, n, &dt);
+  TICK();
+  xcu_setup_local(&dt, &g->d_hall, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
+  xcu_setup_topo_free(&dt);
+  TICK();
+  g->dev_built = 1;
+  g->d_fs = d_fs;
+  g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;      /* counts now, arrays on demand */
+  /* with one rank the interior map is hall itself; hall stays with the handle
+     for the introspection calls */
+  adopt_interior(g, &g->d_hall, 0);
+  TICK();
   xcu_setup_end();
   g->handle_bytes = sizeof *g + ((size_t)g->d_hall.ng + 1 + g->d_hall.ni + g->nfs + 1) * sizeof(u32);
   TICK();
@@ -933,6 +967,56 @@ static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32
     printf("gs_setup profile (device, n=%u): label sort+groups %.3f s, local map+sectors %.3f s, "
            "sliced layout %.3f s, finish %.3f s\n", n, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
 #undef TICK
+}
+
+/* several ranks, device present: the exchange plan (host) has named the
+   boundary groups; the interior/boundary split and both sliced layouts are
+   built in HBM from the device topology.  Same device structures as
+   split_groups() below.                                                     */
+static int upload_boundary_plan(struct gs_data *g, int m);
+static int upload_send_primaries(struct gs_data *g, int m);
+static void split_groups_device(struct gs_data *g, const struct xcu_topo *dt)
+{
+  const struct xg_plan *pl = &g->plan;
+  const u32 nb = pl->nb;
+  struct xcu_dmap in, bnd, bnd2;
+  u32 *d_fs = 0;
+  xcu_setup_split(dt, pl->bgrp, nb, &g->d_hall, &in, &bnd, &bnd2, &g->d_hfp, &g->nfp, &d_fs, &g->nfs,
+                  &g->sectors_f64);
+  g->dev_built = 1;
+  g->d_fs = d_fs;
+  g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;
+  const u32 ing = in.ng, ini = in.ni, bni = bnd.ni;
+  adopt_interior(g, &in, &bnd);
+  xcu_dmap_free(&in);
+  if (nb) {
+    int m = 0;
+    struct xcu_bnd *d = &g->d_bnd;
+    d->nb = nb;
+    g->d_bnd_mem[m] = bnd.off; d->goff = bnd.off; ++m;
+    g->d_bnd_mem[m] = bnd.idx; d->gidx = bnd.idx; ++m;
+    g->d_bnd_mem[m] = bnd.nunf; d->nunf = bnd.nunf; ++m;
+    m = upload_boundary_plan(g, m);
+    const char *bf = getenv("EXAGS_BND_FAST");
+    if (!dt->any_flag && !(bf && atoi(bf) == 0)) {
+      if (bnd2.ng) {
+        struct xcu_dsell bs;
+        xcu_setup_sell(&bnd2, &bs);
+        g->d_brest.c.ng = bs.rest.ng; g->d_brest.c.ni = bs.rest.ni;
+        g->d_brest.off = bs.rest.off; g->d_brest.idx = bs.rest.idx; g->d_brest.nunf = bs.rest.nunf;
+        g->d_brest.c.off = bs.rest.off; g->d_brest.c.idx = bs.rest.idx; g->d_brest.c.nunf = bs.rest.nunf;
+        g->d_bsell.nblock = bs.nblock;
+        g->d_bsell.mask = bs.mask; g->d_bsell.idx = bs.idx;
+        g->d_bnd_mem[m++] = bs.mask; g->d_bnd_mem[m++] = bs.idx;
+        xcu_free(bs.win_min); xcu_free(bs.win_max); xcu_free(bs.fmask);
+      }
+      m = upload_send_primaries(g, m);
+      g->bnd_fast = 1;
+    }
+  } else xcu_dmap_free(&bnd);
+  xcu_dmap_free(&bnd2);
+  xcu_device_sync();
+  g->handle_bytes += ((size_t)ing + 1 + ini + g->nfs + nb + 1 + bni + nb) * sizeof(u32);
 }
 
 /* host copies of a device-built handle's group map, for the introspection calls */
@@ -1010,6 +1094,29 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
     fflush(stdout);
     return g;
   }
+  const int dev_split = np > 1 && setup_on_device(g) && !(lay && strcmp(lay, "csr") == 0);
+  if (dev_split) {
+    /* topology on the device; it also comes back for the shared-label
+       discovery and the exchange plan, which are host code */
+    struct xcu_topo dt;
+    xcu_setup_begin();
+    xcu_setup_topo(id, idbytes, n, &dt);
+    xcu_setup_topo_to_host(&dt, &topo);
+    TICK();
+    xg_shared_discover(&sh, &topo, w);
+    TICK();
+    g->handle_bytes = sizeof *g;
+    xg_plan_build(&g->plan, &sh, &topo);
+    TICK();
+    split_groups_device(g, &dt);
+    xcu_setup_topo_free(&dt);
+    xcu_setup_end();
+    TICK();
+    if (prof)
+      printf("gs_setup profile (rank 0, n=%u, device): label sort+groups+fetch %.3f s, shared discovery %.3f s, "
+             "exchange plan %.3f s, split + sliced layouts %.3f s\n", n,
+             tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
+  } else {
   topo_any(g, &topo, id, idbytes, n);
   xg_shared_discover(&sh, &topo, w);
 
@@ -1024,7 +1131,8 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
   TICK();
   split_groups(g, &topo);
   TICK();
-  if (prof)
+  }
+  if (prof && !dev_split)
     printf("gs_setup profile (rank 0, n=%u): label sort+groups(+shared discovery) %.3f s, local map %.3f s, "
            "sector count %.3f s, exchange plan %.3f s, split + sliced layout + upload %.3f s\n", n,
            tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);

@@ -249,6 +249,18 @@ void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, 
   CU(cudaStreamSynchronize(be.st));
 }
 
+void xcu_setup_split(const struct xcu_topo *t, const u32 *bgrp_host, u32 nb, struct xcu_dmap *hall,
+                     struct xcu_dmap *in, struct xcu_dmap *bnd, struct xcu_dmap *bnd2,
+                     u32 **fp, u32 *nfp, u32 **fs, u32 *nfs, u64 *sectors)
+{
+  Scope sc; CudaBackend &be = sc.be;
+  u32 *bgrp = be.alloc<u32>((size_t)nb + 1);
+  if (nb) CU(cudaMemcpyAsync(bgrp, bgrp_host, (size_t)nb * sizeof(u32), cudaMemcpyHostToDevice, be.st));
+  check(xgsetup::split_maps(be, t, bgrp, nb, hall, in, bnd, bnd2, fp, nfp, fs, nfs, sectors), "interior/boundary split");
+  be.release(bgrp);
+  CU(cudaStreamSynchronize(be.st));
+}
+
 void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
 {
   Scope sc; CudaBackend &be = sc.be;

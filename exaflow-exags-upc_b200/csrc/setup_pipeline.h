@@ -175,36 +175,34 @@ u32 compact_marked(B &be, u32 *sc, size_t n, const u32 *src, const u32 *at, u32 
   return cnt;
 }
 
+// CSR of the groups k with sel[k] & bit, every member, in group order.  sel is
+// a per-group byte of selection bits computed by the caller.  With want_nunf
+// the unflagged member count of each group is recorded too.
 template <class B>
-int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, u32 **fp, u32 *nfp, u32 **fs, u32 *nfs,
-               u64 *sectors)
+int csr_of(B &be, const xcu_topo *t, const unsigned char *sel, unsigned bit, int want_nunf, xcu_dmap *m)
 {
   const size_t ngrp = t->ngrp, nnz = t->nnz;
   const u32 *gstart = t->gstart, *tidx = t->idx, *rowgrp = t->rowgrp;
   const unsigned char *flag = t->flag;
-  hall->ng = hall->ni = 0; hall->off = hall->idx = hall->nunf = 0;
-  *fp = *fs = 0; *nfp = *nfs = 0; *sectors = 0;
-
+  m->ng = m->ni = 0; m->off = m->idx = m->nunf = 0;
   u32 *ks = be.template alloc<u32>(ngrp + 1);    // kept groups before k
   u32 *is = be.template alloc<u32>(ngrp + 1);    // their members before k
   be.for_each(ngrp + 1, [=] XG_DEV(size_t k) {
-    const u32 sz = k < ngrp ? gstart[k + 1] - gstart[k] : 0u;
-    ks[k] = sz >= 2 ? 1u : 0u;
-    is[k] = sz >= 2 ? sz : 0u;
+    const int keep = k < ngrp && (sel[k] & bit);
+    ks[k] = keep ? 1u : 0u;
+    is[k] = keep ? gstart[k + 1] - gstart[k] : 0u;
   });
-  // the member total may exceed 32 bits only if nnz does, which topo_build's
-  // caller has excluded (n < 2^32 - 1)
+  // the member total fits 32 bits because nnz does (n < 2^32 - 1)
   be.scan(ks, ngrp + 1);
   be.scan(is, ngrp + 1);
   const u32 ng = be.get(ks + ngrp), ni = be.get(is + ngrp);
   if ((size_t)ni >= (size_t)XG_NONE) { be.release(ks); be.release(is); return ERR_MAP_TOO_LARGE; }
   u32 *off = be.template alloc<u32>((size_t)ng + 1);
   u32 *idx = be.template alloc<u32>((size_t)ni + 1);
-  u32 *nunf = t->any_flag ? be.template alloc<u32>((size_t)ng + 1) : 0;
+  u32 *nunf = want_nunf ? be.template alloc<u32>((size_t)ng + 1) : 0;
   be.for_each(ngrp, [=] XG_DEV(size_t k) {
-    const u32 a = gstart[k], b = gstart[k + 1];
-    if (b - a < 2) return;
-    const u32 g = ks[k];
+    if (!(sel[k] & bit)) return;
+    const u32 a = gstart[k], b = gstart[k + 1], g = ks[k];
     off[g] = is[k];
     if (nunf) {
       u32 unf = 0;
@@ -214,34 +212,114 @@ int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, u32 **fp, u32 *nfp, u32
   });
   be.for_each(1, [=] XG_DEV(size_t) { off[ng] = ni; });
   be.for_each(nnz, [=] XG_DEV(size_t pos) {
-    const u32 k = rowgrp[pos], a = gstart[k];
-    if (gstart[k + 1] - a < 2) return;
-    idx[is[k] + ((u32)pos - a)] = tidx[pos];
+    const u32 k = rowgrp[pos];
+    if (!(sel[k] & bit)) return;
+    idx[is[k] + ((u32)pos - gstart[k])] = tidx[pos];
   });
   be.release(ks); be.release(is);
-  hall->ng = ng; hall->ni = ni; hall->off = off; hall->idx = idx; hall->nunf = nunf;
+  m->ng = ng; m->ni = ni; m->off = off; m->idx = idx; m->nunf = nunf;
+  return OK;
+}
 
-  if (t->any_flag) {
-    u32 *sc = be.template alloc<u32>(ngrp + 1);
-    be.for_each(ngrp + 1, [=] XG_DEV(size_t k) { sc[k] = (k < ngrp && flag[gstart[k]]) ? 1u : 0u; });
-    *nfp = compact_marked(be, sc, ngrp, tidx, gstart, fp);
-    be.for_each(ngrp + 1, [=] XG_DEV(size_t k) {
-      sc[k] = (k < ngrp && flag[gstart[k]] && gstart[k + 1] - gstart[k] == 1) ? 1u : 0u;
-    });
-    *nfs = compact_marked(be, sc, ngrp, tidx, gstart, fs);
-    be.release(sc);
-  }
+// selection bits of a group
+enum { SEL_ALL2 = 1,      // >= 2 members                                 (hall)
+       SEL_INT2 = 2,      // >= 2 members and not a boundary group        (interior map)
+       SEL_BND = 4,       // boundary group, any size                     (boundary CSR)
+       SEL_BND2 = 8,      // boundary group with >= 2 members             (boundary sliced map)
+       SEL_FP = 16,       // primary flagged                              (flagged_primaries)
+       SEL_FS = 32 };     // primary flagged, single member, not boundary (gs_init list)
 
+// bgrp: nb boundary groups (device array, may be null when nb == 0)
+template <class B>
+unsigned char *select_groups(B &be, const xcu_topo *t, const u32 *bgrp, u32 nb)
+{
+  const size_t ngrp = t->ngrp;
+  const u32 *gstart = t->gstart;
+  const unsigned char *flag = t->flag;
+  unsigned char *sel = be.template alloc<unsigned char>(ngrp + 1);
+  be.zero(sel, ngrp + 1);
+  be.for_each(nb, [=] XG_DEV(size_t b) { sel[bgrp[b]] = SEL_BND; });
+  be.for_each(ngrp, [=] XG_DEV(size_t k) {
+    const u32 a = gstart[k], sz = gstart[k + 1] - a;
+    const unsigned bnd = sel[k] & SEL_BND;
+    unsigned s = bnd;
+    if (sz >= 2) s |= SEL_ALL2 | (bnd ? SEL_BND2 : SEL_INT2);
+    if (flag[a]) s |= SEL_FP | ((sz == 1 && !bnd) ? SEL_FS : 0u);
+    sel[k] = (unsigned char)s;
+  });
+  return sel;
+}
+
+template <class B>
+u32 list_of(B &be, const xcu_topo *t, const unsigned char *sel, unsigned bit, u32 **out)
+{
+  const size_t ngrp = t->ngrp;
+  u32 *sc = be.template alloc<u32>(ngrp + 1);
+  be.for_each(ngrp + 1, [=] XG_DEV(size_t k) { sc[k] = (k < ngrp && (sel[k] & bit)) ? 1u : 0u; });
+  const u32 cnt = compact_marked(be, sc, ngrp, t->idx, t->gstart, out);
+  be.release(sc);
+  return cnt;
+}
+
+template <class B>
+u64 count_sectors(B &be, size_t n, const xcu_dmap *m)
+{
   // distinct 32-byte sectors of a double field that hold a member: members of
   // different groups are distinct indices, so mark and count
-  if (ni) {
-    const size_t nsec = ((size_t)t->n * 8) / 32 + 1;
-    u32 *mark = be.template alloc<u32>(nsec);
-    be.zero(mark, nsec * sizeof(u32));
-    be.for_each(ni, [=] XG_DEV(size_t q) { mark[((size_t)idx[q] * 8) / 32] = 1u; });
-    *sectors = be.sum_u32(mark, nsec);
-    be.release(mark);
+  if (!m->ni) return 0;
+  const u32 *idx = m->idx;
+  const size_t nsec = (n * 8) / 32 + 1;
+  u32 *mark = be.template alloc<u32>(nsec);
+  be.zero(mark, nsec * sizeof(u32));
+  be.for_each(m->ni, [=] XG_DEV(size_t q) { mark[((size_t)idx[q] * 8) / 32] = 1u; });
+  const u64 c = be.sum_u32(mark, nsec);
+  be.release(mark);
+  return c;
+}
+
+// One rank: hall is also the interior map.
+template <class B>
+int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, u32 **fp, u32 *nfp, u32 **fs, u32 *nfs,
+               u64 *sectors)
+{
+  *fp = *fs = 0; *nfp = *nfs = 0; *sectors = 0;
+  unsigned char *sel = select_groups(be, t, (const u32 *)0, 0);
+  const int rc = csr_of(be, t, sel, SEL_ALL2, t->any_flag, hall);
+  if (rc) { be.release(sel); return rc; }
+  if (t->any_flag) {
+    *nfp = list_of(be, t, sel, SEL_FP, fp);
+    *nfs = list_of(be, t, sel, SEL_FS, fs);
   }
+  be.release(sel);
+  *sectors = count_sectors(be, t->n, hall);
+  return OK;
+}
+
+// Several ranks: the exchange plan has named the boundary groups (bgrp,
+// ascending).  hall as above; in = interior groups with >= 2 members; bnd =
+// every boundary group with all its members and unflagged counts; bnd2 = the
+// boundary groups with >= 2 members (built only for maps without flagged
+// labels, where the boundary takes the sliced layout too); fs = flagged single
+// primaries outside the boundary.  Restates the split of split_groups()
+// (gs_host.c) -- the interior/boundary form of local_setup, src/gs.upc:1210-1217.
+template <class B>
+int split_maps(B &be, const xcu_topo *t, const u32 *bgrp, u32 nb, xcu_dmap *hall, xcu_dmap *in,
+               xcu_dmap *bnd, xcu_dmap *bnd2, u32 **fp, u32 *nfp, u32 **fs, u32 *nfs, u64 *sectors)
+{
+  *fp = *fs = 0; *nfp = *nfs = 0; *sectors = 0;
+  bnd2->ng = bnd2->ni = 0; bnd2->off = bnd2->idx = bnd2->nunf = 0;
+  unsigned char *sel = select_groups(be, t, bgrp, nb);
+  int rc = csr_of(be, t, sel, SEL_ALL2, t->any_flag, hall);
+  if (!rc) rc = csr_of(be, t, sel, SEL_INT2, t->any_flag, in);
+  if (!rc) rc = csr_of(be, t, sel, SEL_BND, 1, bnd);
+  if (!rc && !t->any_flag) rc = csr_of(be, t, sel, SEL_BND2, 0, bnd2);
+  if (rc) { be.release(sel); return rc; }
+  if (t->any_flag) {
+    *nfp = list_of(be, t, sel, SEL_FP, fp);
+    *nfs = list_of(be, t, sel, SEL_FS, fs);
+  }
+  be.release(sel);
+  *sectors = count_sectors(be, t->n, hall);
   return OK;
 }
 

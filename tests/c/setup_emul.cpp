@@ -74,6 +74,85 @@ int compare_sell(const xcu_dsell &d, const xg_sell &h)
 }
 }  // namespace
 
+// The interior/boundary split: bgrp = nb group numbers (ascending) standing in
+// for the boundary groups an exchange plan would name.  Expected output from
+// plain loops over the host topology (the rule of split_groups(), gs_host.c).
+extern "C" int setup_emul_split(const void *id, int idbytes, size_t n, const u32 *bgrp, u32 nb, int reverse)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht;
+  xg_topo_build(&ht, wide.data(), n);
+  bool any_flag = false;
+  for (size_t j = 0; j < ht.nnz; ++j) any_flag |= ht.flag[j] != 0;
+  std::vector<u32> in_off, in_idx, in_unf, b_off, b_idx, b_unf, b2_off, b2_idx, fs;
+  {
+    u32 bb = 0;
+    for (size_t g = 0; g < ht.ngrp; ++g) {
+      const u32 a = ht.gstart[g], e = ht.gstart[g + 1];
+      u32 unf = 0;
+      for (u32 j = a; j < e && !ht.flag[j]; ++j) ++unf;
+      if (bb < nb && bgrp[bb] == g) {
+        ++bb;
+        b_off.push_back((u32)b_idx.size()); b_unf.push_back(unf);
+        b_idx.insert(b_idx.end(), ht.idx + a, ht.idx + e);
+        if (e - a >= 2) { b2_off.push_back((u32)b2_idx.size()); b2_idx.insert(b2_idx.end(), ht.idx + a, ht.idx + e); }
+      } else if (e - a >= 2) {
+        in_off.push_back((u32)in_idx.size()); in_unf.push_back(unf);
+        in_idx.insert(in_idx.end(), ht.idx + a, ht.idx + e);
+      } else if (ht.flag[a]) fs.push_back(ht.idx[a]);
+    }
+    in_off.push_back((u32)in_idx.size()); b_off.push_back((u32)b_idx.size()); b2_off.push_back((u32)b2_idx.size());
+  }
+  HostBackend be;
+  be.reverse = reverse != 0;
+  xcu_topo dt;
+  int out = 0;
+  if (xgsetup::topo_build(be, id, idbytes, n, &dt, (u64 *)0)) { xg_topo_free(&ht); return 10; }
+  xcu_dmap hall, in, bnd, bnd2;
+  u32 *dfp = 0, *dfs = 0, dnfp = 0, dnfs = 0;
+  u64 sectors = 0;
+  u32 *dbgrp = be.alloc<u32>((size_t)nb + 1);
+  if (nb) memcpy(dbgrp, bgrp, (size_t)nb * sizeof(u32));
+  if (xgsetup::split_maps(be, &dt, dbgrp, nb, &hall, &in, &bnd, &bnd2, &dfp, &dnfp, &dfs, &dnfs, &sectors)) out = 50;
+  else if (in.ng + 1 != in_off.size() || in.ni != in_idx.size()) out = 51;
+  else if (!same(in.off, in_off.data(), in_off.size()) || !same(in.idx, in_idx.data(), in_idx.size())) out = 52;
+  else if ((in.nunf != 0) != any_flag || (any_flag && !same(in.nunf, in_unf.data(), in_unf.size()))) out = 53;
+  else if (bnd.ng != nb || bnd.ni != b_idx.size()) out = 54;
+  else if (!same(bnd.off, b_off.data(), b_off.size()) || !same(bnd.idx, b_idx.data(), b_idx.size())) out = 55;
+  else if (!bnd.nunf || !same(bnd.nunf, b_unf.data(), b_unf.size())) out = 56;
+  else if (!any_flag && (bnd2.ng + 1 != b2_off.size() || bnd2.ni != b2_idx.size() ||
+                         !same(bnd2.off, b2_off.data(), b2_off.size()) || !same(bnd2.idx, b2_idx.data(), b2_idx.size()))) out = 57;
+  else if (any_flag && (bnd2.ng || bnd2.off)) out = 58;
+  else if (dnfs != fs.size() || (any_flag && !same(dfs, fs.data(), fs.size()))) out = 59;
+  if (!out) {
+    xg_hmap hh;
+    xg_topo_local_map(&ht, 1, &hh);
+    if (hall.ng != hh.ng || hall.ni != hh.ni || !same(hall.idx, hh.idx, hh.ni) || sectors != host_sectors(&hh)) out = 60;
+    xg_hmap_free(&hh);
+  }
+  if (out != 50) {
+    xgsetup::dmap_release(be, &hall); xgsetup::dmap_release(be, &in);
+    xgsetup::dmap_release(be, &bnd); xgsetup::dmap_release(be, &bnd2);
+  }
+  be.release(dfp); be.release(dfs); be.release(dbgrp);
+  xgsetup::topo_release(be, &dt);
+  xg_topo_free(&ht);
+  return out;
+}
+
+// group count of the host topology (so a test can pick boundary groups)
+extern "C" size_t setup_emul_ngroups(const void *id, int idbytes, size_t n)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht;
+  xg_topo_build(&ht, wide.data(), n);
+  const size_t g = ht.ngrp;
+  xg_topo_free(&ht);
+  return g;
+}
+
 // Returns 0 when every array matches, else a stage code (10s topology, 20s
 // local map, 30s flagged lists / sectors, 40s sliced layout).
 extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int reverse)

@@ -93,6 +93,15 @@ def main():
     elif what in ("exec", "exech"):
         onhost = what == "exech"
         import itertools
+        # the maps of a handle built on the device (topology, interior/boundary
+        # split) against the oracle's, like the CPU-only "setup" mode
+        dumps = gather_arrays([g.dump_map(w) for w in range(5)], np_)
+        if rank == 0:
+            for r in range(np_):
+                for w in range(5):
+                    if not np.array_equal(dumps[r][w], orc.map(r, w)):
+                        print(f"MISMATCH case={case} rank={r} map={w} (device-built handle)")
+                        ok = False
         combos = list(itertools.product(cases.DTYPES.items(), cases.OPS, (0, 1), (0, 1, 2)))
         for (dname, dt), op, t, mode in combos:
             vn = 1 if mode == 0 else 3

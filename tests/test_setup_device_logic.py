@@ -34,10 +34,24 @@ def emul():
     L.setup_emul_compare.restype = ctypes.c_int
     L.setup_emul_compare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
 
+    L.setup_emul_split.restype = ctypes.c_int
+    L.setup_emul_split.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                   ctypes.c_uint, ctypes.c_int]
+    L.setup_emul_ngroups.restype = ctypes.c_size_t
+    L.setup_emul_ngroups.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
+
+    def split(ids, frac, seed, reverse=0):
+        ids = np.ascontiguousarray(ids)
+        ng = L.setup_emul_ngroups(ids.ctypes.data, ids.dtype.itemsize, ids.size)
+        rng = np.random.default_rng(seed)
+        bgrp = np.flatnonzero(rng.random(ng) < frac).astype(np.uint32)
+        return L.setup_emul_split(ids.ctypes.data, ids.dtype.itemsize, ids.size, bgrp.ctypes.data, bgrp.size, reverse)
+
     def run(ids, reverse=0):
         ids = np.ascontiguousarray(ids)
         assert ids.dtype in (np.int64, np.int32)
         return L.setup_emul_compare(ids.ctypes.data, ids.dtype.itemsize, ids.size, reverse)
+    run.split = split
     return run
 
 
@@ -92,3 +106,19 @@ def test_window_boundaries(emul):
 def test_large_labels(emul):
     ids = np.array([2**61, 5, -(2**61), 2**40, 5, 2**40, 0, 1], np.int64)
     assert emul(ids) == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("frac", [0.0, 0.2, 1.0])
+def test_interior_boundary_split(emul, seed, frac):
+    """A random subset of the groups plays the boundary an exchange plan names."""
+    ids = cases.random_ids(2500 + 97 * seed, 600, 40 + seed, p_flag=0.0 if seed % 2 else 0.25,
+                           long_group=30 if seed % 3 == 0 else 0)
+    assert emul.split(ids, frac, seed) == 0
+    assert emul.split(ids, frac, seed, reverse=1) == 0
+
+
+def test_interior_boundary_split_mesh(emul):
+    ids = semmesh.box_ids(6, 5, 4, 5)
+    assert emul.split(ids, 0.1, 1) == 0
+    assert emul.split(np.zeros(0, np.int64), 0.5, 2) == 0
