@@ -115,6 +115,7 @@ struct xg_sell {
   struct xg_hmap rest;/* groups with more than XG_SELL_WMAX members          */
 };
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m);
+int  xg_sell_pairs_enabled(void);
 void xg_sell_free(struct xg_sell *s);
 void xg_topo_local_map(const struct xg_topo *t, int all, struct xg_hmap *m);
 u32 *xg_topo_flagged_primaries(const struct xg_topo *t, int singles_only, u32 *count);

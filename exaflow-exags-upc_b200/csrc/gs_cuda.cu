@@ -227,18 +227,45 @@ k_fused(xcu_csr m, Fld<T, MODE> f, int transpose)
 // ONE: all components fit one pass (vn <= KU), so component numbers are
 // compile-time constants and gs_many's pointer table is read with constant
 // indices.
+// Phase (csrc/sell_window.h, xg_sell_pair_order): the odd bits of a lane's
+// start mask are never group starts; bit 2j+1 set means "fetch the pair in
+// slots (2j, 2j+1) partner first".  swap_pairs exchanges bits / values 2j and
+// 2j+1 where that bit is set, so that load and store instruction j of the
+// warp touches the partner in such lanes and the primary in the others --
+// the two then share a 128-byte line by construction of the layout.  The
+// values go back to slot order before the reduction: results do not depend on
+// the phase.
+__device__ __forceinline__ unsigned swap_pair_bits(unsigned m, unsigned ph)
+{
+  const unsigned hi = ph & 0xAAu, lo = hi >> 1, both = hi | lo;
+  return (m & ~both) | ((m & lo) << 1) | ((m & hi) >> 1);
+}
+
 template <typename T, int OP, int MODE, int KU, bool GONLY = false, bool FLG = false, bool ONE = false>
 __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
-                                          const unsigned start, const unsigned flg = 0u,
+                                          const unsigned startph, const unsigned flg = 0u,
                                           const int transpose = 0)
 {
-  const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  const unsigned start = startph & 0x55u, ph = startph & 0xAAu;
   unsigned in = 0u, out = 0u;                 // slots that contribute / are written
 #pragma unroll
-  for (int j = 0; j < 8; ++j) if (id[j] != XG_NONE) in |= 1u << j;
+  for (int j = 0; j < 8; ++j) if (id0[j] != XG_NONE) in |= 1u << j;
   out = in;
   if (FLG) { if (transpose) out = in & (~flg | start); else in &= ~flg; }
   if (GONLY) out &= start;
+  // everything below addresses memory in "fetch order": id[], lin, lout
+  u32 id[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const bool sw = (ph >> (j + 1)) & 1u;
+    id[j] = sw ? id0[j + 1] : id0[j];
+    id[j + 1] = sw ? id0[j] : id0[j + 1];
+  }
+  // a phase bit is only ever set on a complete pair: without flags both of its
+  // slots contribute and both are written, so the masks need no swapping
+  const unsigned lin = FLG ? swap_pair_bits(in, ph) : in;
+  const unsigned lout = (FLG || GONLY) ? swap_pair_bits(out, ph) : out;
   const size_t es = f.stride();
   for (unsigned k0 = 0; k0 < (ONE ? 1u : f.vn); k0 += KU) {
     T x[KU][8];
@@ -251,11 +278,18 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (FLG) x[kk][j] = ident<T, OP>();
-          if ((in >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
+          if ((lin >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
         }
       }
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk) {
+      // fetch order -> slot order
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const bool sw = (ph >> (j + 1)) & 1u;
+        const T p0 = x[kk][j], p1 = x[kk][j + 1];
+        x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
+      }
       // forward: running reduction, restarted where a group begins
 #pragma unroll
       for (int j = 1; j < 8; ++j) {
@@ -265,13 +299,20 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
       // backward: the last slot of a group holds its total; spread it
 #pragma unroll
       for (int j = 6; j >= 0; --j) x[kk][j] = ((start >> (j + 1)) & 1u) ? x[kk][j] : x[kk][j + 1];
+      // slot order -> fetch order
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const bool sw = (ph >> (j + 1)) & 1u;
+        const T p0 = x[kk][j], p1 = x[kk][j + 1];
+        x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk)
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if ((out >> j) & 1u) pk[kk][id[j] * es] = x[kk][j];
+          if ((lout >> j) & 1u) pk[kk][id[j] * es] = x[kk][j];
       }
   }
 }
@@ -309,8 +350,16 @@ k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
   const uint4 a = __ldg(p), b = __ldg(p + 1);
-  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
-  const u32 id[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
+  const unsigned start = startph & 0x55u, ph = startph & 0xAAu;   // see swap_pair_bits
+  const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+  u32 id[8];                                   // fetch order
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const bool sw = (ph >> (j + 1)) & 1u;
+    id[j] = sw ? id0[j + 1] : id0[j];
+    id[j + 1] = sw ? id0[j] : id0[j + 1];
+  }
   T x[3][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -324,12 +373,24 @@ k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
 #pragma unroll
   for (int kk = 0; kk < 3; ++kk) {
 #pragma unroll
+    for (int j = 0; j < 8; j += 2) {           // fetch order -> slot order
+      const bool sw = (ph >> (j + 1)) & 1u;
+      const T p0 = x[kk][j], p1 = x[kk][j + 1];
+      x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
+    }
+#pragma unroll
     for (int j = 1; j < 8; ++j) {
-      const T cont = (id[j] != XG_NONE) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
+      const T cont = (id0[j] != XG_NONE) ? apply<T, OP>(x[kk][j - 1], x[kk][j]) : x[kk][j - 1];
       x[kk][j] = ((start >> j) & 1u) ? x[kk][j] : cont;
     }
 #pragma unroll
     for (int j = 6; j >= 0; --j) x[kk][j] = ((start >> (j + 1)) & 1u) ? x[kk][j] : x[kk][j + 1];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {           // slot order -> fetch order
+      const bool sw = (ph >> (j + 1)) & 1u;
+      const T p0 = x[kk][j], p1 = x[kk][j + 1];
+      x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j)

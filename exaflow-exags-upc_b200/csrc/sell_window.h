@@ -24,6 +24,80 @@
 
 XG_HD static inline u32 xg_sell_width(u32 size) { return size <= 2 ? 2u : size <= 4 ? 4u : 8u; }
 
+/* Dealing order of a window's pairs (groups of exactly two members), and a
+   phase bit for each.
+
+   A lane loads its 8 slots with 8 load instructions; instruction j of a warp
+   therefore touches slot j of 32 different lanes, and costs one trip through
+   L1 per distinct 128-byte line among those 32 addresses.  On a hexahedral
+   spectral-element mesh the pairs across an x-face are {last node of a row of
+   element e, first node of the same row of element e+1}: dealt in primary
+   order, the 32 primaries of an instruction lie in 32 different rows, one or
+   two useful values per line.  Two things put more of them into one line:
+
+   twins    two pairs whose primaries share a line and whose partners share a
+            line (rows r and r+1 of the same face) go to neighbouring lanes;
+   chains   the pair that continues the same row in the next element --
+            its primary lies in the line of this pair's partner -- comes next,
+            with the opposite phase.  A lane of phase 1 loads its pair as
+            (partner, primary) instead of (primary, partner), so the partner of
+            one unit and the primary of the next, which share a line, are
+            fetched by the same instruction.  The values are put back in slot
+            order before the reduction, so nothing else changes.
+
+   Purely an ordering of lanes inside a window plus a load schedule: every
+   group keeps its members, their order and its window.  Meshes without this
+   structure get chains of length one, i.e. the plain primary order.
+
+   chain == 0 switches the reordering off (EXAGS_SELL_PAIRS=0, for A/B runs).
+   ord[t] = position (k - first) of the t-th pair to deal, ph[t] its phase;
+   returns the number of pairs.  Lines are taken as 16 elements (128 bytes of
+   doubles; for 4-byte fields that is half a line, which still shares).      */
+XG_HD static inline u32 xg_sell_pair_order(u32 first, u32 last, const u32 *sg, const u32 *off,
+                                           const u32 *idx, unsigned short *ord, unsigned char *ph,
+                                           int chain)
+{
+  unsigned short ck[XG_SELL_WSLOTS / 2];          /* pairs in primary order: k - first */
+  u32 P[XG_SELL_WSLOTS / 2], Q[XG_SELL_WSLOTS / 2];
+  u32 used[XG_SELL_WSLOTS / 64];
+  u32 M = 0, ne = 0;
+  for (u32 k = first; k < last; ++k) {
+    const u32 a = off[sg[k]];
+    if (off[sg[k] + 1] - a != 2) continue;
+    if (M == XG_SELL_WSLOTS / 2) break;           /* cannot happen: 2 slots each */
+    ck[M] = (unsigned short)(k - first); P[M] = idx[a]; Q[M] = idx[a + 1]; ++M;
+  }
+  if (!chain) {                                   /* plain primary order, no phases */
+    for (u32 s = 0; s < M; ++s) { ord[s] = ck[s]; ph[s] = 0; }
+    return M;
+  }
+  for (u32 z = 0; z < XG_SELL_WSLOTS / 64; ++z) used[z] = 0;
+#define XG_USED(s_) ((used[(s_) >> 5] >> ((s_) & 31u)) & 1u)
+#define XG_MARK(s_) (used[(s_) >> 5] |= 1u << ((s_) & 31u))
+  for (u32 s = 0; s < M; ++s) {
+    if (XG_USED(s)) continue;
+    u32 cur = s;
+    unsigned char phase = 0;
+    for (;;) {
+      XG_MARK(cur); ord[ne] = ck[cur]; ph[ne] = phase; ++ne;
+      const u32 tw = cur + 1;                      /* twin: the next pair in primary order */
+      if (tw < M && !XG_USED(tw) && (P[tw] >> 4) == (P[cur] >> 4) && (Q[tw] >> 4) == (Q[cur] >> 4)) {
+        XG_MARK(tw); ord[ne] = ck[tw]; ph[ne] = phase; ++ne;
+      }
+      /* successor: first unused pair whose primary lies in the partner's line
+         (P ascends: binary search for the start of the line) */
+      const u32 line = Q[cur] >> 4;
+      u32 lo = 0, hi = M;
+      while (lo < hi) { const u32 mid = lo + (hi - lo) / 2; if ((P[mid] >> 4) < line) lo = mid + 1; else hi = mid; }
+      while (lo < M && (P[lo] >> 4) == line && XG_USED(lo)) ++lo;
+      if (lo < M && (P[lo] >> 4) == line) { cur = lo; phase ^= 1; } else break;
+    }
+  }
+#undef XG_USED
+#undef XG_MARK
+  return ne;
+}
+
 /* off/idx/nunf: CSR of the map the groups come from (nunf may be NULL);
    out_idx, mask, fmask (may be NULL), win_min, win_max: the arrays of struct
    xg_sell, indexed from their start.  Returns 0, or 1 when the groups handed
@@ -31,7 +105,7 @@ XG_HD static inline u32 xg_sell_width(u32 size) { return size <= 2 ? 2u : size <
 XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const u32 *sg,
                                             const u32 *off, const u32 *idx, const u32 *nunf,
                                             u32 *out_idx, unsigned char *mask, unsigned char *fmask,
-                                            u32 *win_min, u32 *win_max)
+                                            u32 *win_min, u32 *win_max, int chain)
 {
   unsigned char fill[XG_SELL_LANES];
   u32 *base = out_idx + w * XG_SELL_WSLOTS;
@@ -49,9 +123,18 @@ XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const
       }
     win_min[w] = lo; win_max[w] = hi;
   }
+  /* Pairs (the faces of a mesh: by far the most groups) are dealt in an order
+     that lets one load instruction of the warp find several of its 32 members
+     in the same 128-byte line, see xg_sell_pair_order().  ord2/ph2 list the
+     window's pairs in dealing order with the phase of each.                 */
+  unsigned short ord2[XG_SELL_WSLOTS / 2];
+  unsigned char ph2[XG_SELL_WSLOTS / 2];
+  const u32 n2 = xg_sell_pair_order(first, last, sg, off, idx, ord2, ph2, chain);
   for (u32 wd = 8; wd >= 2; wd >>= 1) {
     u32 pos = 0;                                  /* lane cursor over the window */
-    for (u32 k = first; k < last; ++k) {
+    const u32 count = wd == 2 ? n2 : last - first;
+    for (u32 t = 0; t < count; ++t) {
+      const u32 k = wd == 2 ? first + ord2[t] : first + t;
       const u32 g = sg[k], a = off[g], sz = off[g + 1] - a;
       if (xg_sell_width(sz) != wd) continue;
       /* next lane (block-major, then lane) with room; fills are multiples of
@@ -64,6 +147,9 @@ XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const
       u32 *slot = base + (size_t)pos * 8 + fill[pos];
       for (u32 q = 0; q < sz; ++q) slot[q] = idx[a + q];
       mk[pos] = (unsigned char)(mk[pos] | (1u << fill[pos]));
+      /* a pair never starts at an odd slot, so the odd bits of the start mask
+         are free: bit 2j+1 carries the phase of the pair in slots (2j, 2j+1) */
+      if (wd == 2 && ph2[t]) mk[pos] = (unsigned char)(mk[pos] | (2u << fill[pos]));
       if (fk) {                                   /* members [nunf, sz) are flagged */
         const u32 unf = nunf[g];
         fk[pos] = (unsigned char)(fk[pos] | ((((1u << sz) - 1u) & ~((1u << unf) - 1u)) << fill[pos]));

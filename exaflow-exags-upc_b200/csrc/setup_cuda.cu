@@ -264,7 +264,7 @@ void xcu_setup_split(const struct xcu_topo *t, const u32 *bgrp_host, u32 nb, str
 void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
 {
   Scope sc; CudaBackend &be = sc.be;
-  check(xgsetup::sell_build(be, m, s), "sliced layout");
+  check(xgsetup::sell_build(be, m, s, xg_sell_pairs_enabled()), "sliced layout");
   CU(cudaStreamSynchronize(be.st));
 }
 

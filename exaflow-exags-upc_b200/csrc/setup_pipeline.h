@@ -334,7 +334,7 @@ void dmap_release(B &be, xcu_dmap *m)
 // sliced-ELL layout of a CSR map (struct xg_sell, exags_internal.h)
 // ---------------------------------------------------------------------------
 template <class B>
-int sell_build(B &be, const xcu_dmap *m, xcu_dsell *s)
+int sell_build(B &be, const xcu_dmap *m, xcu_dsell *s, int chain = 1)
 {
   const u32 ng = m->ng;
   const u32 *off = m->off, *idx = m->idx, *nunf = m->nunf;
@@ -428,7 +428,7 @@ int sell_build(B &be, const xcu_dmap *m, xcu_dsell *s)
   be.zero(mask + (size_t)nblock * 32, 1);
   if (fmask) be.zero(fmask + (size_t)nblock * 32, 1);
   be.for_each(nwin, [=] XG_DEV(size_t w) {
-    if (xg_sell_fill_window(w, wfirst[w], wfirst[w + 1], sg, off, idx, nunf, oidx, mask, fmask, wmin, wmax))
+    if (xg_sell_fill_window(w, wfirst[w], wfirst[w + 1], sg, off, idx, nunf, oidx, mask, fmask, wmin, wmax, chain))
       cnt[1] = 1u;
   });
   const u32 bad = be.get(cnt + 1);

@@ -250,6 +250,13 @@ void xg_sell_free(struct xg_sell *s)
 #include "sell_window.h"
 #define sell_width xg_sell_width
 
+/* EXAGS_SELL_PAIRS=0: deal pairs in plain primary order (sell_window.h) */
+int xg_sell_pairs_enabled(void)
+{
+  const char *e = getenv("EXAGS_SELL_PAIRS");
+  return !(e && atoi(e) == 0);
+}
+
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
 {
   const u32 WSLOTS = XG_SELL_WB * 256u;            /* member slots per window */
@@ -315,12 +322,13 @@ void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)
   if (m->nunf) s->fmask = xnew0(unsigned char, (size_t)s->nblock * 32 + 1);
   s->idx = xnew(u32, s->nidx ? s->nidx : 1);
   int bad = 0;
+  const int chain = xg_sell_pairs_enabled();
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 64) num_threads(xg_setup_threads()) reduction(| : bad)
 #endif
   for (size_t w = 0; w < nwin; ++w)
     bad |= xg_sell_fill_window(w, wfirst[w], wfirst[w + 1], sg, m->off, m->idx, m->nunf,
-                               s->idx, s->mask, s->fmask, s->win_min, s->win_max);
+                               s->idx, s->mask, s->fmask, s->win_min, s->win_max, chain);
   if (bad) xfail("gs_setup: internal error packing the sliced layout");
   free(wfirst); free(sg);
 }

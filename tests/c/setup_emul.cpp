@@ -141,6 +141,38 @@ extern "C" int setup_emul_split(const void *id, int idbytes, size_t n, const u32
   return out;
 }
 
+// Trips through L1 the field loads of one gs() make with this layout: distinct
+// 128-byte lines (of a double field) per load instruction of a warp, summed
+// over blocks and slots, honouring the phase bits.  A planning figure for the
+// pair ordering of sell_window.h, not a test.
+extern "C" unsigned long long setup_emul_line_visits(const void *id, int idbytes, size_t n)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht; xg_topo_build(&ht, wide.data(), n);
+  xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
+  xg_sell hs; xg_sell_build(&hs, &hh);
+  unsigned long long visits = 0;
+  for (u32 b = 0; b < hs.nblock; ++b)
+    for (int j = 0; j < 8; ++j) {
+      u32 lines[32]; int nl = 0;
+      for (int lane = 0; lane < 32; ++lane) {
+        const size_t L = (size_t)b * 32 + lane;
+        const unsigned ph = hs.mask[L] & 0xAAu;
+        const int slot = ((ph >> ((j | 1))) & 1u) ? (j ^ 1) : j;
+        const u32 v = hs.idx[L * 8 + slot];
+        if (v == XG_NONE) continue;
+        const u32 line = v >> 4;
+        bool seen = false;
+        for (int q = 0; q < nl; ++q) if (lines[q] == line) { seen = true; break; }
+        if (!seen) lines[nl++] = line;
+      }
+      visits += nl;
+    }
+  xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
+  return visits;
+}
+
 // group count of the host topology (so a test can pick boundary groups)
 extern "C" size_t setup_emul_ngroups(const void *id, int idbytes, size_t n)
 {
@@ -198,7 +230,7 @@ extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int rev
   } else if (hnfp || hnfs) { out = 32; goto done; }
   if (sectors != host_sectors(&hh)) { out = 33; goto done; }
 
-  rc = xgsetup::sell_build(be, &dh, &ds);
+  rc = xgsetup::sell_build(be, &dh, &ds, xg_sell_pairs_enabled());
   if (rc) { out = 39; goto done; }
   out = compare_sell(ds, hs);
 done:
