@@ -775,7 +775,7 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   } else if (mode == XM_VEC && f->vn == 3 && f->tuple == 3 && f->k0 == 0 &&
              ((uintptr_t)f->p[0] % (2 * (xdom == XD_F64 || xdom == XD_I64 ? 8 : 4))) == 0) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell_vec3<T, OP, (sizeof(T) == 8 ? 3 : 4)><<<grid, nthr, 0, st>>>(*m, (T *)f->p[0])
+  k_fused_sell_vec3<T, OP, (sizeof(T) == 8 ? 3 : 6)><<<grid, nthr, 0, st>>>(*m, (T *)f->p[0])
     FOR_DOM(XM_VEC, X)
 #undef X
   } else if (mode == XM_VEC) {
@@ -785,7 +785,7 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
 #undef X
   } else if (f->vn <= 3) {
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 3), false, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), 0)
+  k_fused_sell<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 4), false, false, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), 0)
     FOR_DOM(XM_MANY, X)
 #undef X
   } else {
