@@ -173,6 +173,59 @@ extern "C" unsigned long long setup_emul_line_visits(const void *id, int idbytes
   return visits;
 }
 
+// The sliced layout decodes back to the map it was built from: every group of
+// at most 8 members appears exactly once, members in order, inside a lane, in
+// the window that holds its primary-order neighbours; longer groups are in the
+// residual CSR; phase bits (odd mask bits) sit only on pairs.  0 = ok.
+extern "C" int setup_emul_sell_roundtrip(const void *id, int idbytes, size_t n)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht; xg_topo_build(&ht, wide.data(), n);
+  xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
+  xg_sell hs; xg_sell_build(&hs, &hh);
+  int out = 0;
+  // groups found in the layout: (primary, first slot position)
+  std::vector<std::pair<u32, size_t>> found;
+  for (size_t L = 0; L < (size_t)hs.nblock * 32 && !out; ++L) {
+    const unsigned mk = hs.mask[L], start = mk & 0x55u, ph = mk & 0xAAu;
+    const u32 *sl = hs.idx + L * 8;
+    for (int j = 0; j < 8; ++j) {
+      if (sl[j] == XG_NONE) { if ((start >> j) & 1u) out = 70; continue; }
+      if (j == 0 && !(start & 1u)) out = 71;                 // a used lane starts with a group
+      if ((start >> j) & 1u) found.push_back({sl[j], L * 8 + j});
+    }
+    for (int j = 0; j < 8; j += 2)
+      if ((ph >> (j + 1)) & 1u) {                              // phase only on a complete pair
+        const bool pair = ((start >> j) & 1u) && sl[j] != XG_NONE && sl[j + 1] != XG_NONE &&
+                          (j + 2 == 8 || sl[j + 2] == XG_NONE || ((start >> (j + 2)) & 1u));
+        if (!pair) out = 72;
+      }
+  }
+  std::sort(found.begin(), found.end());
+  size_t f = 0, r = 0;
+  for (u32 g = 0; g < hh.ng && !out; ++g) {
+    const u32 a = hh.off[g], sz = hh.off[g + 1] - a;
+    if (sz > XG_SELL_WMAX) {
+      if (r >= hs.rest.ng || hs.rest.off[r + 1] - hs.rest.off[r] != sz ||
+          memcmp(hs.rest.idx + hs.rest.off[r], hh.idx + a, sz * sizeof(u32))) out = 73;
+      ++r;
+      continue;
+    }
+    if (f >= found.size() || found[f].first != hh.idx[a]) { out = 74; break; }
+    const size_t pos = found[f].second;
+    if ((pos & 7) + sz > 8) { out = 75; break; }               // inside one lane
+    if (memcmp(hs.idx + pos, hh.idx + a, sz * sizeof(u32))) { out = 76; break; }
+    // the slot after the group is free, a new group, or the lane's end
+    if ((pos & 7) + sz < 8 && hs.idx[pos + sz] != XG_NONE && !((hs.mask[pos >> 3] >> ((pos & 7) + sz)) & 1u)) { out = 77; break; }
+    if (hs.win_min[pos / XG_SELL_WSLOTS] > hh.idx[a] || hs.win_max[pos / XG_SELL_WSLOTS] < hh.idx[a + sz - 1]) { out = 78; break; }
+    ++f;
+  }
+  if (!out && (f != found.size() || r != hs.rest.ng)) out = 79;
+  xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
+  return out;
+}
+
 // group count of the host topology (so a test can pick boundary groups)
 extern "C" size_t setup_emul_ngroups(const void *id, int idbytes, size_t n)
 {
