@@ -24,8 +24,10 @@
 
 XG_HD static inline u32 xg_sell_width(u32 size) { return size <= 2 ? 2u : size <= 4 ? 4u : 8u; }
 
-/* Dealing order of a window's pairs (groups of exactly two members), and a
-   phase bit for each.
+/* Dealing order of the groups of one width class of a window, and a phase bit
+   for each.  Written for pairs (groups of exactly two members), where it
+   matters most; wider groups are ordered by their first two members in the same
+   way, and their phase applies to every complete slot pair of the group.
 
    A lane loads its 8 slots with 8 load instructions; instruction j of a warp
    therefore touches slot j of 32 different lanes, and costs one trip through
@@ -49,25 +51,26 @@ XG_HD static inline u32 xg_sell_width(u32 size) { return size <= 2 ? 2u : size <
    group keeps its members, their order and its window.  Meshes without this
    structure get chains of length one, i.e. the plain primary order.
 
-   chain == 0 switches the reordering off (EXAGS_SELL_PAIRS=0, for A/B runs).
-   ord[t] = position (k - first) of the t-th pair to deal, ph[t] its phase;
-   returns the number of pairs.  Lines are taken as 16 elements (128 bytes of
+   chain: 0 switches the reordering off, 1 applies it to pairs only, 2 to every
+   width class (EXAGS_SELL_PAIRS, for A/B runs).
+   ord[t] = position (k - first) of the t-th group to deal, ph[t] its phase;
+   returns the number of groups of the class.  Lines are taken as 16 elements (128 bytes of
    doubles; for 4-byte fields that is half a line, which still shares).      */
-XG_HD static inline u32 xg_sell_pair_order(u32 first, u32 last, const u32 *sg, const u32 *off,
-                                           const u32 *idx, unsigned short *ord, unsigned char *ph,
-                                           int chain)
+XG_HD static inline u32 xg_sell_class_order(u32 first, u32 last, const u32 *sg, const u32 *off,
+                                            const u32 *idx, u32 wd, unsigned short *ord,
+                                            unsigned char *ph, int chain)
 {
-  unsigned short ck[XG_SELL_WSLOTS / 2];          /* pairs in primary order: k - first */
+  unsigned short ck[XG_SELL_WSLOTS / 2];          /* the class in primary order: k - first */
   u32 P[XG_SELL_WSLOTS / 2], Q[XG_SELL_WSLOTS / 2];
   u32 used[XG_SELL_WSLOTS / 64];
   u32 M = 0, ne = 0;
   for (u32 k = first; k < last; ++k) {
     const u32 a = off[sg[k]];
-    if (off[sg[k] + 1] - a != 2) continue;
-    if (M == XG_SELL_WSLOTS / 2) break;           /* cannot happen: 2 slots each */
+    if (xg_sell_width(off[sg[k] + 1] - a) != wd) continue;
+    if (M == XG_SELL_WSLOTS / 2) break;           /* cannot happen: >= 2 slots each */
     ck[M] = (unsigned short)(k - first); P[M] = idx[a]; Q[M] = idx[a + 1]; ++M;
   }
-  if (!chain) {                                   /* plain primary order, no phases */
+  if (!chain || (chain == 1 && wd != 2)) {        /* plain primary order, no phases */
     for (u32 s = 0; s < M; ++s) { ord[s] = ck[s]; ph[s] = 0; }
     return M;
   }
@@ -123,18 +126,17 @@ XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const
       }
     win_min[w] = lo; win_max[w] = hi;
   }
-  /* Pairs (the faces of a mesh: by far the most groups) are dealt in an order
-     that lets one load instruction of the warp find several of its 32 members
-     in the same 128-byte line, see xg_sell_pair_order().  ord2/ph2 list the
-     window's pairs in dealing order with the phase of each.                 */
-  unsigned short ord2[XG_SELL_WSLOTS / 2];
-  unsigned char ph2[XG_SELL_WSLOTS / 2];
-  const u32 n2 = xg_sell_pair_order(first, last, sg, off, idx, ord2, ph2, chain);
+  /* Groups are dealt, class by class, in an order that lets one load
+     instruction of the warp find several of its 32 members in the same
+     128-byte line, see xg_sell_class_order().  ordc/phc list the class in
+     dealing order with the phase of each group.                             */
+  unsigned short ordc[XG_SELL_WSLOTS / 2];
+  unsigned char phc[XG_SELL_WSLOTS / 2];
   for (u32 wd = 8; wd >= 2; wd >>= 1) {
     u32 pos = 0;                                  /* lane cursor over the window */
-    const u32 count = wd == 2 ? n2 : last - first;
+    const u32 count = xg_sell_class_order(first, last, sg, off, idx, wd, ordc, phc, chain);
     for (u32 t = 0; t < count; ++t) {
-      const u32 k = wd == 2 ? first + ord2[t] : first + t;
+      const u32 k = first + ordc[t];
       const u32 g = sg[k], a = off[g], sz = off[g + 1] - a;
       if (xg_sell_width(sz) != wd) continue;
       /* next lane (block-major, then lane) with room; fills are multiples of
@@ -147,9 +149,11 @@ XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const
       u32 *slot = base + (size_t)pos * 8 + fill[pos];
       for (u32 q = 0; q < sz; ++q) slot[q] = idx[a + q];
       mk[pos] = (unsigned char)(mk[pos] | (1u << fill[pos]));
-      /* a pair never starts at an odd slot, so the odd bits of the start mask
-         are free: bit 2j+1 carries the phase of the pair in slots (2j, 2j+1) */
-      if (wd == 2 && ph2[t]) mk[pos] = (unsigned char)(mk[pos] | (2u << fill[pos]));
+      /* a group never starts at an odd slot, so the odd bits of the start mask
+         are free: bit 2j+1 carries the phase of slots (2j, 2j+1).  Only slot
+         pairs that hold two members of the group get one. */
+      if (phc[t])
+        for (u32 q = 0; q + 1 < sz; q += 2) mk[pos] = (unsigned char)(mk[pos] | (2u << (fill[pos] + q)));
       if (fk) {                                   /* members [nunf, sz) are flagged */
         const u32 unf = nunf[g];
         fk[pos] = (unsigned char)(fk[pos] | ((((1u << sz) - 1u) & ~((1u << unf) - 1u)) << fill[pos]));

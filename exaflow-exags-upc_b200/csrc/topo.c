@@ -250,11 +250,13 @@ void xg_sell_free(struct xg_sell *s)
 #include "sell_window.h"
 #define sell_width xg_sell_width
 
-/* EXAGS_SELL_PAIRS=0: deal pairs in plain primary order (sell_window.h) */
+/* EXAGS_SELL_PAIRS: 0 deals every class in plain primary order, 1 chains the
+   pairs only, 2 (default) every width class (sell_window.h)                */
 int xg_sell_pairs_enabled(void)
 {
   const char *e = getenv("EXAGS_SELL_PAIRS");
-  return !(e && atoi(e) == 0);
+  const int v = e ? atoi(e) : 2;
+  return v < 0 ? 0 : v > 2 ? 2 : v;
 }
 
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)

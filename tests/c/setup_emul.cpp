@@ -196,10 +196,8 @@ extern "C" int setup_emul_sell_roundtrip(const void *id, int idbytes, size_t n)
       if ((start >> j) & 1u) found.push_back({sl[j], L * 8 + j});
     }
     for (int j = 0; j < 8; j += 2)
-      if ((ph >> (j + 1)) & 1u) {                              // phase only on a complete pair
-        const bool pair = ((start >> j) & 1u) && sl[j] != XG_NONE && sl[j + 1] != XG_NONE &&
-                          (j + 2 == 8 || sl[j + 2] == XG_NONE || ((start >> (j + 2)) & 1u));
-        if (!pair) out = 72;
+      if ((ph >> (j + 1)) & 1u) {          // phase only where both slots hold members of one group
+        if (sl[j] == XG_NONE || sl[j + 1] == XG_NONE) out = 72;
       }
   }
   std::sort(found.begin(), found.end());

@@ -139,7 +139,7 @@ def test_interior_boundary_split_mesh(emul):
     assert emul.split(np.zeros(0, np.int64), 0.5, 2) == 0
 
 
-@pytest.mark.parametrize("pairs", ["1", "0"])
+@pytest.mark.parametrize("pairs", ["2", "1", "0"])
 def test_sliced_layout_decodes_to_the_map(emul, pairs, monkeypatch):
     """The layout (with and without the pair ordering) holds every group once,
     members in order, and phase bits only on pairs."""
@@ -164,4 +164,6 @@ def test_pair_ordering_reduces_line_visits(emul, monkeypatch):
     monkeypatch.setenv("EXAGS_SELL_PAIRS", "0")
     plain = emul.visits(ids)
     monkeypatch.setenv("EXAGS_SELL_PAIRS", "1")
-    assert emul.visits(ids) < 0.92 * plain
+    pairs_only = emul.visits(ids)
+    monkeypatch.setenv("EXAGS_SELL_PAIRS", "2")
+    assert emul.visits(ids) < pairs_only < 0.92 * plain
