@@ -101,7 +101,12 @@ void xg_hmap_free(struct xg_hmap *m);
    No per-group offsets remain: 4 bytes per member + 1 mask byte per lane.
    Groups with more than 8 members stay in a residual CSR.                   */
 #define XG_SELL_WMAX 8
-#define XG_SELL_WB   8     /* blocks per window = warps per CTA */
+#ifndef XG_SELL_WB
+#define XG_SELL_WB   8     /* blocks per window (a multiple of XG_SELL_CW)            */
+#endif
+#define XG_SELL_CW   8     /* blocks per CTA of the sliced kernels = warps per CTA.
+                              Measured: a window split over two CTAs loses the L1
+                              reuse the chain order creates (profiles/r1_sweep10) */
 struct xg_sell {
   u32  nblock;        /* multiple of XG_SELL_WB                              */
   unsigned char *mask;/* [nblock*32] start mask of each lane                 */

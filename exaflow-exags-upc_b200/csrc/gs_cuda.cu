@@ -318,10 +318,10 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
 }
 
 template <typename T, int OP, int MODE, int KU, int MINB, bool GONLY = false, bool FLG = false, bool ONE = false>
-__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
 k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
 {
-  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
+  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
   const uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -342,11 +342,11 @@ template <> struct Pair<int>       { typedef int2 type; };
 template <> struct Pair<long long> { typedef longlong2 type; };
 
 template <typename T, int OP, int MINB>
-__global__ void __launch_bounds__(32 * XG_SELL_WB, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
 k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
 {
   typedef typename Pair<T>::type T2;
-  const u32 c = blockIdx.x * (u32)XG_SELL_WB + (threadIdx.x >> 5);
+  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
   const uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -737,8 +737,8 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
 {
   if (!m->nblock) return;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = m->nblock / XG_SELL_WB;
-  const unsigned nthr = 32 * XG_SELL_WB;
+  const unsigned grid = m->nblock / XG_SELL_CW;
+  const unsigned nthr = 32 * XG_SELL_CW;
   if (m->fmask) {
     /* maps with flagged members: same kernel with the flag mask */
     if (mode == XM_PLAIN || f->vn == 1) {
@@ -802,8 +802,8 @@ void xcu_gather_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mo
 {
   if (!m->nblock) return;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = m->nblock / XG_SELL_WB;
-  const unsigned nthr = 32 * XG_SELL_WB;
+  const unsigned grid = m->nblock / XG_SELL_CW;
+  const unsigned nthr = 32 * XG_SELL_CW;
   if (mode == XM_PLAIN || f->vn == 1) {
     xcu_field f1 = *f;
     f1.vn = 1; f1.tuple = 1;
