@@ -53,6 +53,7 @@ struct CudaBackend {
   int dev = -1;
   int depth = 0;
   cudaMemPool_t pool = nullptr;
+  unsigned long long saved_threshold = 0;
 
   void begin()
   {
@@ -67,7 +68,10 @@ struct CudaBackend {
       if (!res_h) CU(cudaMallocHost(&res_h, 64));
     }
     if (!res) CU(cudaMalloc(&res, 64));
+    /* keep freed blocks for the length of the setup; the application's own
+       setting comes back in end() */
     unsigned long long keep = ~0ull;
+    CU(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &saved_threshold));
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   void end()
@@ -76,9 +80,8 @@ struct CudaBackend {
     CU(cudaStreamSynchronize(st));
     if (tmp) { CU(cudaFreeAsync(tmp, st)); tmp = nullptr; tmp_bytes = 0; }
     CU(cudaStreamSynchronize(st));
-    unsigned long long keep = 0;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    CU(cudaMemPoolTrimTo(pool, 0));
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &saved_threshold));
+    CU(cudaMemPoolTrimTo(pool, (size_t)saved_threshold));
     xcu_note_launches(launches);
     launches = 0;
   }
