@@ -12,6 +12,7 @@
  * other directly, so the same rendezvous ("work rank" = id mod np) is done
  * with one all-to-all over the host shared-memory segment each way.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "exags_internal.h"
@@ -37,6 +38,11 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
   const int np = xg_world_np(w), me = xg_world_rank(w);
   memset(out, 0, sizeof *out);
   if (np == 1) return;
+  const char *prof_env = getenv("EXAGS_SETUP_PROFILE");
+  const int prof = prof_env && atoi(prof_env) >= 2 && me == 0;
+  double tp[8]; int ntp = 0;
+#define TICK() do { if (prof) exags_comm_time(&tp[ntp++]); } while (0)
+  TICK();
 
   /* Which of my labels can another rank hold at all?  The reference ships every
      local label to its work rank (src/gs.upc:118-131); on a spectral-element
@@ -77,6 +83,7 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
 #undef LABEL_BIT
     free(others);
   }
+  TICK();
 
   /* one row per candidate label, grouped by work rank id % np (src/gs.upc:118-131) */
   size_t *cnt = xnew0(size_t, np), *pos = xnew(size_t, np);
@@ -93,9 +100,11 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
     r->pad = 0;
   }
   free(cand);
+  TICK();
   size_t *rcnt = xnew(size_t, np), nrecv = 0;
   struct uq_row *un = (struct uq_row *)xg_host_alltoallv(w, send, sizeof *send, cnt, rcnt, &nrecv);
   free(send);
+  TICK();
 
   /* work rank: group by id with unflagged rows ahead of flagged ones
      (src/gs.upc:204).  Rows arrive ordered by source rank. */
@@ -182,6 +191,11 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
     s->flags = (is_flagged(back[k].i1f) ? XG_FLAGS_LOCAL : 0u) | (is_flagged(back[k].i2f) ? XG_FLAGS_REMOTE : 0u);
   }
   free(back);
+  TICK();
+  if (prof)
+    printf("shared discovery (rank 0): presence bitmaps %.3f s, candidate rows %.3f s, to work ranks %.3f s, "
+           "pairing + return %.3f s\n", tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
+#undef TICK
 }
 
 /* sort shared rows by (p, id): the globally consistent message order
