@@ -53,8 +53,64 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
      so the rows the work ranks pair up -- and everything derived from them --
      are exactly the reference's.                                            */
   unsigned char *cand = xnew(unsigned char, t->ngrp ? t->ngrp : 1);
+  const int nthr = xg_setup_threads();
+  (void)nthr;
   {
-    u64 mine_n = t->ngrp, *all_n = xnew(u64, np), maxn = 1;
+    /* Stage 1, coarse: the label space [0, global max] is cut into XG_BINS
+       equal bins and every rank publishes which bins it has labels in (8 KB).
+       A label in a bin no other rank occupies cannot be shared.  With the
+       lexicographic numbering of a partitioned mesh this already leaves little
+       more than the interface labels, and the table stays in L1 -- the hashed
+       bitmap below, whose random accesses miss the caches, then sees only
+       those.  A shared label passes on both of its ranks (each sees the other's
+       bin), so the filter never loses one.                                   */
+    enum { XG_BINS = 65536 };
+    u64 lmax = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(max : lmax) num_threads(nthr)
+#endif
+    for (size_t g = 0; g < t->ngrp; ++g) if (t->id[g] > lmax) lmax = t->id[g];
+    u64 *all_max = xnew(u64, np), gmax = 0;
+    xg_host_allgather(w, &lmax, sizeof lmax, all_max);
+    for (int p = 0; p < np; ++p) if (all_max[p] > gmax) gmax = all_max[p];
+    free(all_max);
+    unsigned shift = 0;
+    while ((gmax >> shift) >= (u64)XG_BINS) ++shift;
+    u64 *bins = xnew0(u64, XG_BINS / 64), *all_bins = xnew(u64, (size_t)np * (XG_BINS / 64));
+    /* few distinct words, hit over and over: plain loop per thread, merged */
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthr)
+#endif
+    {
+      u64 *loc = xnew0(u64, XG_BINS / 64);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+      for (size_t g = 0; g < t->ngrp; ++g) { const u64 b = t->id[g] >> shift; loc[b >> 6] |= (u64)1 << (b & 63); }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+      for (size_t k = 0; k < XG_BINS / 64; ++k) bins[k] |= loc[k];
+      free(loc);
+    }
+    xg_host_allgather(w, bins, (XG_BINS / 64) * sizeof(u64), all_bins);
+    memset(bins, 0, (XG_BINS / 64) * sizeof(u64));
+    for (int p = 0; p < np; ++p)
+      if (p != me) for (size_t k = 0; k < XG_BINS / 64; ++k) bins[k] |= all_bins[(size_t)p * (XG_BINS / 64) + k];
+    free(all_bins);
+    u64 npass = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : npass) num_threads(nthr)
+#endif
+    for (size_t g = 0; g < t->ngrp; ++g) {
+      const u64 b = t->id[g] >> shift;
+      cand[g] = (unsigned char)((bins[b >> 6] >> (b & 63)) & 1u);
+      npass += cand[g];
+    }
+    free(bins);
+
+    /* Stage 2, fine: presence bitmap over a hash of the labels that passed */
+    u64 mine_n = npass, *all_n = xnew(u64, np), maxn = 1;
     xg_host_allgather(w, &mine_n, sizeof mine_n, all_n);
     for (int p = 0; p < np; ++p) if (all_n[p] > maxn) maxn = all_n[p];
     free(all_n);
@@ -62,13 +118,12 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
     while (bits < 34 && ((u64)1 << bits) < 16 * maxn) ++bits;       /* <= 1/16 full: ~6 % false positives */
     const size_t words = (size_t)1 << (bits - 6);
     u64 *mine = xg_host_bitmap_new(w, words), *others = xnew(u64, words);
-    const int nthr = xg_setup_threads();
-    (void)nthr;
 #define LABEL_BIT(id_) (((id_) * 0x9E3779B97F4A7C15ull) >> (64 - bits))
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(nthr)
 #endif
     for (size_t g = 0; g < t->ngrp; ++g) {
+      if (!cand[g]) continue;
       const u64 h = LABEL_BIT(t->id[g]);
       __atomic_fetch_or(&mine[h >> 6], (u64)1 << (h & 63), __ATOMIC_RELAXED);
     }
@@ -77,6 +132,7 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
 #pragma omp parallel for schedule(static) num_threads(nthr)
 #endif
     for (size_t g = 0; g < t->ngrp; ++g) {
+      if (!cand[g]) continue;
       const u64 h = LABEL_BIT(t->id[g]);
       cand[g] = (unsigned char)((others[h >> 6] >> (h & 63)) & 1u);
     }
