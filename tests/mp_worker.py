@@ -32,6 +32,19 @@ def make_ids(case, np_, rank):
         return semmesh.block_partition_ids(4, 4, 4, 2, 2, 2, 2, np_, rank)[0]
     if case == "random":
         return cases.random_ids(700 + 31 * rank, 300, 99 + rank)
+    if case == "sparse":     # huge, widely spaced labels: the coarse label-range filter of
+        # the shared-label discovery works with a large bin width; a few labels sit
+        # in bins that only one rank occupies, most are shared
+        rng = np.random.default_rng(7)
+        pool = np.sort(rng.choice(2**20, size=400, replace=False)).astype(np.int64) * (2**38) + 5
+        mine = rng.permutation(np.concatenate([pool[rank::2], pool[::3], pool[:40]]))
+        lone = (2**60 + 1000 * rank + np.arange(15)).astype(np.int64)
+        return np.concatenate([mine, lone, np.zeros(3, np.int64)])
+    if case == "clustered":  # each rank's labels in its own range, overlapping the next rank's by a few
+        base = 10**6 * rank
+        own = base + np.arange(1, 3001, dtype=np.int64)
+        nxt = 10**6 * (rank + 1) + np.arange(1, 41, dtype=np.int64)      # shared with rank+1
+        return np.concatenate([own, nxt, own[:500]])
     if case == "empty":      # rank 1 owns nothing
         return cases.random_ids(0 if rank == 1 else 200, 80, 5 + rank)
     raise SystemExit(f"unknown case {case}")

@@ -64,7 +64,8 @@ def test_unique_np1(X, O):
 
 @pytest.mark.parametrize("np_,case", [(2, "fixture"), (2, "slab"), (3, "random"), (4, "blocks"),
                                       (2, "empty"), (4, "fixture"), (8, "blocks"), (8, "fixture"),
-                                      (5, "random"), (4, "bigslab"), (3, "bigblocks")])
+                                      (5, "random"), (4, "bigslab"), (3, "bigblocks"),
+                                      (2, "sparse"), (3, "sparse"), (4, "clustered"), (2, "clustered")])
 def test_multirank_setup(built, np_, case):
     codes, outs = run_ranks(np_, [case, "setup"])
     assert all(c == 0 for c in codes), "\n".join(outs)
