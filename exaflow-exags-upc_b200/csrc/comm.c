@@ -758,15 +758,24 @@ void exags_comm_scan(void *scan, const comm_ptr cp, gs_dom dom, gs_op_t op,
   if (xd < 0) xfail("comm_scan: bad domain %d", (int)dom);
   struct xg_world *w = (struct xg_world *)cp->priv;
   size_t bytes = (size_t)vn * xg_dom_bytes(xd);
-  char *all = (char *)xmalloc_(bytes * (size_t)cp->np, __FILE__, __LINE__);
-  xg_host_allgather(w, v, bytes, all);
-  char *excl = (char *)scan, *tot = (char *)scan + bytes;
+  /* v and scan may each be a host vector (the reference's contract) or a device
+     vector: scans carry a few counters per rank, so device vectors are folded
+     on the host in rank order like host ones */
+  const int v_dev = w->has_cuda && xcu_is_device_ptr(v);
+  const int s_dev = w->has_cuda && xcu_is_device_ptr(scan);
+  char *all = (char *)xmalloc_(bytes * ((size_t)cp->np + 3), __FILE__, __LINE__);
+  char *mine = all + bytes * (size_t)cp->np, *out = mine + bytes;
+  if (v_dev) { xcu_device_sync(); xcu_d2h(mine, v, bytes, 0); xcu_device_sync(); }
+  else memcpy(mine, v, bytes);
+  xg_host_allgather(w, mine, bytes, all);
+  char *excl = s_dev ? out : (char *)scan, *tot = excl + bytes;
   host_identity(excl, vn, xd, (int)op);
   host_identity(tot, vn, xd, (int)op);
   for (int p = 0; p < cp->np; ++p) {
     if (p < cp->id) host_combine(excl, all + (size_t)p * bytes, vn, xd, (int)op);
     host_combine(tot, all + (size_t)p * bytes, vn, xd, (int)op);
   }
+  if (s_dev) { xcu_h2d(scan, out, 2 * bytes, 0); xcu_device_sync(); }
   free(all);
 }
 

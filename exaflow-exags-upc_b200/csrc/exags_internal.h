@@ -197,6 +197,7 @@ void   xcu_stream_destroy(void *s);
 void   xcu_stream_sync(void *s);
 void  *xcu_event_create(void);
 void  *xcu_event_create_timed(void);
+void   xcu_event_destroy(void *ev);
 float  xcu_event_ms(void *a, void *b);
 void   xcu_event_record(void *ev, void *stream);
 void   xcu_stream_wait_event(void *stream, void *ev);
@@ -218,6 +219,8 @@ struct xcu_field {
   unsigned vn;           /* components handled by this launch               */
   unsigned tuple;        /* vec: elements per tuple in memory (>= vn)       */
   unsigned k0;           /* vec: first component handled by this launch     */
+  const void *w;         /* weights T[n] of the weighted gs (exags_cuda.h), plain
+                            float/double fields only; NULL otherwise          */
 };
 
 /* device CSR */

@@ -241,11 +241,16 @@ __device__ __forceinline__ unsigned swap_pair_bits(unsigned m, unsigned ph)
   return (m & ~both) | ((m & lo) << 1) | ((m & hi) >> 1);
 }
 
-template <typename T, int OP, int MODE, int KU, bool GONLY = false, bool FLG = false, bool ONE = false>
+// WGT: weighted gs (exags_gs_weighted, include/exags_cuda.h) -- the value stored
+// to a member is the group's result times wgt[member]; the weights are fetched
+// together with the field so that both loads are in flight at once.
+template <typename T, int OP, int MODE, int KU, bool GONLY = false, bool FLG = false, bool ONE = false,
+          bool WGT = false>
 __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
                                           const unsigned startph, const unsigned flg = 0u,
-                                          const int transpose = 0)
+                                          const int transpose = 0, const T *__restrict__ wgt = nullptr)
 {
+  static_assert(!WGT || (KU == 1 && MODE == XM_PLAIN && !GONLY), "weights: plain fields, full gather-scatter");
   const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   const unsigned start = startph & 0x55u, ph = startph & 0xAAu;
   unsigned in = 0u, out = 0u;                 // slots that contribute / are written
@@ -281,6 +286,14 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
           if ((lin >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
         }
       }
+    T wv[WGT ? 8 : 1];
+    if (WGT) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wv[WGT ? j : 0] = (T)1;
+        if ((lout >> j) & 1u) wv[WGT ? j : 0] = __ldg(wgt + id[j]);
+      }
+    }
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk) {
       // fetch order -> slot order
@@ -312,7 +325,7 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if ((lout >> j) & 1u) pk[kk][id[j] * es] = x[kk][j];
+          if ((lout >> j) & 1u) pk[kk][id[j] * es] = WGT ? x[kk][j] * wv[WGT ? j : 0] : x[kk][j];
       }
   }
 }
@@ -328,6 +341,38 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const unsigned flg = FLG ? __ldg(m.fmask + (size_t)c * 32u + lane) : 0u;
   sell_lane<T, OP, MODE, KU, GONLY, FLG, ONE>(f, a, b, start, flg, transpose);
+}
+
+// Weighted form of the two local kernels (exags_gs_weighted: Nek's dssum
+// followed by a multiplication with the inverse multiplicity, fused): plain
+// float/double fields.  8 more bytes per member are read (the weight), against
+// a separate pass over the whole field (read u, read w, write u).
+template <typename T, int OP, int MINB, bool FLG>
+__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+k_fused_sell_w(xcu_sell m, Fld<T, XM_PLAIN> f, const T *__restrict__ wgt, int transpose)
+{
+  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
+  const unsigned flg = FLG ? __ldg(m.fmask + (size_t)c * 32u + lane) : 0u;
+  sell_lane<T, OP, XM_PLAIN, 1, false, FLG, false, true>(f, a, b, start, flg, transpose, wgt);
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+k_fused_w(xcu_csr m, T *__restrict__ u, const T *__restrict__ wgt, int transpose)
+{
+  u32 g = blockIdx.x * 256u + threadIdx.x;
+  if (g >= m.ng) return;
+  u32 b = __ldg(m.off + g), e = __ldg(m.off + g + 1);
+  u32 nall = e - b, nunf = m.nunf ? __ldg(m.nunf + g) : nall, nred, nwr;
+  group_counts(nall, nunf, transpose, nred, nwr);
+  const u32 *idx = m.idx + b;
+  T v = nred ? u[__ldg(idx)] : ident<T, OP>();
+  for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, u[__ldg(idx + j)]);
+  for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
 }
 
 // gs_vec with 3-tuples (a velocity field, BASELINE config 3): a tuple is 3
@@ -583,6 +628,30 @@ k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ re
   }
 }
 
+// weighted form (plain float/double fields): what the unpack writes to a member
+// is the group's result times the member's weight
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+k_bnd_unpack_w(xcu_bnd bd, T *__restrict__ u, const T *__restrict__ wgt, int transpose,
+               const T *__restrict__ recvbuf, int allreduce)
+{
+  for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
+    u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
+    u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
+    group_counts(nall, nunf, transpose, nred, nwr);
+    const u32 *idx = bd.gidx + gb;
+    const int rd = 0 ^ transpose;
+    T v = u[__ldg(idx)];
+    if (allreduce) {
+      if (!transpose || !bd.pflag[b]) v = recvbuf[__ldg(bd.ord + b)];
+    } else {
+      const u32 rb = __ldg(bd.soff[rd] + b), re = __ldg(bd.soff[rd] + b + 1);
+      for (u32 s = rb; s < re; ++s) v = apply<T, OP>(v, recvbuf[__ldg(bd.slot[rd] + s)]);
+    }
+    for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_fill(T *__restrict__ out, size_t n, T v)
 {
@@ -715,6 +784,22 @@ static inline unsigned bnd_blocks(size_t nb)
     default: exags_fail(1, __FILE__, __LINE__, "gs: bad mode %d", mode);      \
   }
 
+/* weighted gs: float/double only */
+#define FOR_OP_W(T, X)                                                        \
+  switch (xop) {                                                              \
+    case XO_ADD: X(T, XO_ADD); break;                                         \
+    case XO_MUL: X(T, XO_MUL); break;                                         \
+    case XO_MIN: X(T, XO_MIN); break;                                         \
+    case XO_MAX: X(T, XO_MAX); break;                                         \
+    default: exags_fail(1, __FILE__, __LINE__, "gs_weighted: bad op %d", xop); \
+  }
+#define FOR_DOM_W(X)                                                          \
+  switch (xdom) {                                                             \
+    case XD_F64: FOR_OP_W(double, X); break;                                  \
+    case XD_F32: FOR_OP_W(float, X); break;                                   \
+    default: exags_fail(1, __FILE__, __LINE__, "gs_weighted: floating-point domains only (got %d)", xdom); \
+  }
+
 extern "C" {
 
 unsigned long long xcu_launch_count(void) { return g_launches; }
@@ -724,6 +809,13 @@ void xcu_fused(void *stream, const xcu_csr *m, const xcu_field *f, int mode, int
 {
   if (!m->ng) return;
   cudaStream_t st = (cudaStream_t)stream;
+  if (f->w) {
+#define X(T, OP) k_fused_w<T, OP><<<blocks_for(m->ng), 256, 0, st>>>(*m, (T *)f->p[0], (const T *)f->w, transpose)
+    FOR_DOM_W(X)
+#undef X
+    LAUNCHED();
+    return;
+  }
 #define X(T, OP, MODE)                                                        \
   k_fused<T, OP, MODE><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fld<T, MODE>(f), transpose)
   FOR_ALL(X)
@@ -739,6 +831,22 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = m->nblock / XG_SELL_CW;
   const unsigned nthr = 32 * XG_SELL_CW;
+  if (f->w) {
+    /* weighted gs: plain float/double fields (checked by the caller) */
+    xcu_field f1 = *f;
+    f1.vn = 1; f1.tuple = 1;
+    if (m->fmask) {
+#define X(T, OP) k_fused_sell_w<T, OP, 4, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, transpose)
+      FOR_DOM_W(X)
+#undef X
+    } else {
+#define X(T, OP) k_fused_sell_w<T, OP, 4, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, 0)
+      FOR_DOM_W(X)
+#undef X
+    }
+    LAUNCHED();
+    return;
+  }
   if (m->fmask) {
     /* maps with flagged members: same kernel with the flag mask */
     if (mode == XM_PLAIN || f->vn == 1) {
@@ -916,6 +1024,13 @@ void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode
 {
   if (!b->nb) return;
   cudaStream_t st = (cudaStream_t)stream;
+  if (f->w) {
+#define X(T, OP) k_bnd_unpack_w<T, OP><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, (T *)f->p[0], (const T *)f->w, transpose, (const T *)recvbuf, allreduce)
+    FOR_DOM_W(X)
+#undef X
+    LAUNCHED();
+    return;
+  }
 #define X(T, OP, MODE)                                                        \
   k_bnd_unpack<T, OP, MODE><<<bnd_blocks(b->nb), 256, 0, st>>>(               \
       *b, make_fld<T, MODE>(f), transpose, (const T *)recvbuf, bufvn, allreduce)
@@ -1059,6 +1174,7 @@ void *xcu_event_create_timed(void)
   CU(cudaEventCreate(&e));
   return (void *)e;
 }
+void xcu_event_destroy(void *ev) { if (ev) CU(cudaEventDestroy((cudaEvent_t)ev)); }
 float xcu_event_ms(void *a, void *b)
 {
   float ms = 0;

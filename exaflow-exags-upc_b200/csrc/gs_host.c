@@ -345,7 +345,7 @@ static void bnd_pack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, in
 
 /* exchange (or wait for the neighbours' stores) + unpack and scatter */
 static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, int mode, unsigned vn,
-                       int xd, int xop, int transpose, void *scomm)
+                       int xd, int xop, int transpose, void *scomm, const void *wgt)
 {
   struct xg_world *w = g->w;
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
@@ -359,6 +359,7 @@ static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, 
   else exchange_pairwise(g, vn, xd, transpose, c->sendbuf, c->recvbuf, scomm);
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
+    f.w = wgt;
     xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, c->recvbuf, vn, c->allred);
   }
 }
@@ -369,10 +370,10 @@ static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, 
 static int g_trace = -1;
 static double g_trace_ms[5]; static unsigned long g_trace_calls;
 static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                             int xd, int xop, int transpose, void *stream);
+                             int xd, int xop, int transpose, void *stream, const void *wgt);
 
 static void gs_enqueue_traced(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                              int xd, int xop, int transpose, void *stream)
+                              int xd, int xop, int transpose, void *stream, const void *wgt)
 {
   static void *ev[6];
   if (!ev[0]) for (int i = 0; i < 6; ++i) ev[i] = xcu_event_create_timed();
@@ -383,9 +384,9 @@ static void gs_enqueue_traced(struct gs_data *g, void *const *ptrs, int mode, un
   xcu_event_record(ev[1], stream);
   if (bc.active) bnd_pack_phase(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream, 2);
   xcu_event_record(ev[2], stream);
-  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream);
+  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream, wgt);
   xcu_event_record(ev[3], stream);
-  if (bc.active) bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream);
+  if (bc.active) bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream, wgt);
   xcu_event_record(ev[4], stream);
   xcu_stream_sync(stream);
   /* the first launches of a kernel instantiation include module loading */
@@ -407,11 +408,12 @@ static void trace_report(struct gs_data *g)
 }
 
 static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                             int xd, int xop, int transpose, void *stream)
+                             int xd, int xop, int transpose, void *stream, const void *wgt)
 {
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
+    f.w = wgt;      /* weighted gs: the stores of the group results carry the weight */
     if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
@@ -421,13 +423,13 @@ static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, uns
 /* Enqueue one gs on device-resident data.  ptrs: vn device pointers for
    mode many, else ptrs[0].  Work is ordered on `stream`.                   */
 static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                       int xd, int xop, int transpose, void *stream)
+                       int xd, int xop, int transpose, void *stream, const void *wgt)
 {
   struct xg_world *w = g->w;
   struct bnd_ctx bc;
   void *scomm = xg_world_stream(w, 1);
   if (g_trace < 0) { const char *v = getenv("EXAGS_TRACE"); g_trace = v ? atoi(v) : 0; }
-  if (g_trace > 0) { gs_enqueue_traced(g, ptrs, mode, vn, xd, xop, transpose, stream); return; }
+  if (g_trace > 0) { gs_enqueue_traced(g, ptrs, mode, vn, xd, xop, transpose, stream, wgt); return; }
   bnd_prepare(g, &bc, vn, xd, transpose);
   if (bc.active) {
     /* fork: boundary stream starts after whatever precedes us on `stream` */
@@ -436,9 +438,9 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
     bnd_pack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
   }
   /* interior: fused gather-scatter on the caller's stream */
-  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream);
+  interior_enqueue(g, ptrs, mode, vn, xd, xop, transpose, stream, wgt);
   if (bc.active) {
-    bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm);
+    bnd_unpack(g, &bc, ptrs, mode, vn, xd, xop, transpose, scomm, wgt);
     /* join */
     xcu_event_record(xg_world_event(w, 1), scomm);
     xcu_stream_wait_event(stream, xg_world_event(w, 1));
@@ -527,7 +529,7 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
     if (k == C - 1 && bc.active) {
       xcu_stream_wait_event(scomm, g->pipe_ev[k]);
       bnd_pack(g, &bc, dptr, mode, vn, xd, xop, transpose, scomm);
-      bnd_unpack(g, &bc, dptr, mode, vn, xd, xop, transpose, scomm);
+      bnd_unpack(g, &bc, dptr, mode, vn, xd, xop, transpose, scomm, 0);
       xcu_event_record(xg_world_event(w, 1), scomm);
     }
     for (unsigned j = 0; j < C; ++j) {
@@ -583,7 +585,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   }
 
   if (!host) {
-    gs_enqueue(g, ptrs, mode, vn, xd, op, (int)transpose, stream);
+    gs_enqueue(g, ptrs, mode, vn, xd, op, (int)transpose, stream, 0);
     if (blocking) { xcu_stream_sync(stream); push_check(g, "during this call"); }
     free(ptrs);
     return;
@@ -606,7 +608,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   } else {
     dptr[0] = stage; xcu_h2d(stage, u, total, stream);
   }
-  gs_enqueue(g, dptr, mode, vn, xd, op, (int)transpose, stream);
+  gs_enqueue(g, dptr, mode, vn, xd, op, (int)transpose, stream, 0);
   if (mode == XM_MANY) for (unsigned k = 0; k < vn; ++k) xcu_d2h(ptrs[k], dptr[k], each, stream);
   else xcu_d2h(u, stage, total, stream);
   xcu_stream_sync(stream);
@@ -632,6 +634,35 @@ void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op, unsigned tr
   if (mode == XM_PLAIN) vn = 1;
   gs_run(u, mode, vn, dom, op, transpose, gsh, stream, 0, "gs_async");
 }
+
+/* Weighted gs (extension, include/exags_cuda.h): what Nek issues
+   as dssum followed by a multiplication with the inverse multiplicity, in the
+   one pass over the field that gs makes anyway.  Device vectors, plain
+   float/double fields, transpose 0.                                          */
+static void gs_run_weighted(void *u, const void *wgt, int dom, int op, struct gs_data *g,
+                            void *stream, int blocking, const char *who)
+{
+  int xd;
+  if (!g) xfail("%s: null handle", who);
+  check_dom_op(dom, op, &xd, who);
+  if (xd != XD_F64 && xd != XD_F32) xfail("%s: floating-point domains only (got %d)", who, dom);
+  if (op > XO_MAX) xfail("%s: op %d not in valid range", who, op);
+  if (!g->on_device)
+    xfail("%s: no CUDA device -- this library has no CPU execution path", who);
+  if (!g->n) return;
+  if (!xcu_is_device_ptr(u) || !xcu_is_device_ptr(wgt))
+    xfail("%s: u and w must be device vectors", who);
+  if (blocking) stream = xg_world_stream(g->w, 0);
+  void *ptrs[1] = { u };
+  gs_enqueue(g, ptrs, XM_PLAIN, 1, xd, op, 0, stream, wgt);
+  if (blocking) { xcu_stream_sync(stream); push_check(g, "during this call"); }
+}
+
+void exags_gs_weighted(void *u, const void *w, int dom, int op, struct gs_data *gsh)
+{ gs_run_weighted(u, w, dom, op, gsh, 0, 1, "gs_weighted"); }
+
+void exags_gs_weighted_async(void *u, const void *w, int dom, int op, struct gs_data *gsh, void *stream)
+{ gs_run_weighted(u, w, dom, op, gsh, stream, 0, "gs_weighted_async"); }
 
 /* the Nek flavour shares the operator; only the id width differs */
 void gslib_gs(void *u, int dom, int op, unsigned t, struct gs_data *g, buffer *b)
@@ -1212,6 +1243,7 @@ void exags_gs_free(struct gs_data *g)
     xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);
     if (g->dev_built) { xcu_dmap_free(&g->d_hall); xcu_free(g->d_hfp); }
+    for (unsigned k = 0; g->pipe_ev && k < 2 * g->pipe_chunks; ++k) xcu_event_destroy(g->pipe_ev[k]);
   }
   xg_hmap_free(&g->hall);
   free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);

@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.exags_comm_scan.argtypes = [vp, comm_ptr, i32, i32, vp, u32, vp]
     L.exags_comm_dot.argtypes = [comm_ptr, vp, vp, u32]
     L.exags_comm_dot.restype = C.c_double
+    L.exags_comm_bcast.argtypes = [comm_ptr, vp, C.c_size_t, u32]
     L.gslib_gs_setup.argtypes = [vp, u32, comm_ptr, i32, i32, i32]
     L.gslib_gs_setup.restype = vp
     L.exags_gs_setup.argtypes = [vp, u32, comm_ptr, i32, i32, i32]
@@ -85,6 +86,10 @@ def lib() -> C.CDLL:
         getattr(L, name).restype = None
     L.exags_gs_async.argtypes = [vp, i32, u32, i32, i32, u32, vp, vp]
     L.exags_gs_async.restype = None
+    L.exags_gs_weighted.argtypes = [vp, vp, i32, i32, vp]
+    L.exags_gs_weighted.restype = None
+    L.exags_gs_weighted_async.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.exags_gs_weighted_async.restype = None
     L.gslib_gs_free.argtypes = [vp]
     L.exags_gs_free.argtypes = [vp]
     L.gslib_gs_unique.argtypes = [vp, u32, comm_ptr]
@@ -219,6 +224,14 @@ def gs_async(u, mode: int, vn: int, dom: int, op: int, transpose: int, gsh: GS, 
         lib().exags_gs_async(_addr(u), mode, vn, dom, op, transpose, gsh.ptr, stream)
 
 
+def gs_weighted(u, w, dom: int, op: int, gsh: GS, stream: int | None = None) -> None:
+    """u <- w .* gs(u, op) in one pass (include/exags_cuda.h); device vectors."""
+    if stream is None:
+        lib().exags_gs_weighted(_addr(u), _addr(w), dom, op, gsh.ptr)
+    else:
+        lib().exags_gs_weighted_async(_addr(u), _addr(w), dom, op, gsh.ptr, stream)
+
+
 def gs_free(gsh: GS) -> None:
     if gsh.ptr:
         lib().gslib_gs_free(gsh.ptr)
@@ -251,6 +264,22 @@ def comm_allreduce(v, dom: int, op: int, comm=None) -> None:
     """comm_allreduce(cp, dom, op, v, vn, buf) in place (src/comm.upc:831)."""
     n = v.numel() if hasattr(v, "numel") else v.size
     lib().exags_comm_allreduce(comm if comm is not None else comm_world(), dom, op, _addr(v), n, None)
+
+
+def comm_scan(v, dom: int, op: int, comm=None, out=None):
+    """comm_scan(scan, cp, dom, op, v, vn, buf) (src/comm.upc:706): returns
+    (exclusive prefix over lower ranks, total over all ranks).  v: host array or
+    device tensor; out: optional device tensor / host array of 2*vn elements."""
+    n = v.numel() if hasattr(v, "numel") else v.size
+    if out is None:
+        out = np.empty(2 * n, dtype=DOM_NP[dom])
+    lib().exags_comm_scan(_addr(out), comm if comm is not None else comm_world(), dom, op, _addr(v), n, None)
+    return out[:n], out[n:]
+
+
+def comm_bcast(buf: np.ndarray, root: int, comm=None) -> None:
+    """comm_bcast(cp, p, n, root) (src/comm.upc:427): bytes of a host array, in place."""
+    lib().exags_comm_bcast(comm if comm is not None else comm_world(), buf.ctypes.data, buf.nbytes, root)
 
 
 def kernel_launches() -> int:

@@ -22,6 +22,21 @@ extern "C" {
 void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op,
                     unsigned transpose, struct gs_data *gsh, void *stream);
 
+/* Weighted gs: u <- w .* gs(u, op) in one pass over the field -- the pair
+   "dssum, then multiply by the inverse multiplicity" that Nek5000 issues around
+   the reference's gs, without the second pass.  Every value gs
+   writes as the result of a group (to each member of a group of two or more
+   DOFs, counted over all ranks) is multiplied by w at that member's index;
+   DOFs that share their label with nobody are not touched, so the call equals
+   gs() followed by u[i] *= w[i] whenever w[i] == 1 off the shared nodes, as an
+   inverse-multiplicity weight is.  u and w are device vectors T[n] of the same
+   floating-point dom (gs_double or gs_float); plain fields, transpose 0.
+   exags_gs_weighted blocks like gs(); the _async form is ordered on `stream`
+   like exags_gs_async.                                                       */
+void exags_gs_weighted(void *u, const void *w, int dom, int op, struct gs_data *gsh);
+void exags_gs_weighted_async(void *u, const void *w, int dom, int op,
+                             struct gs_data *gsh, void *stream);
+
 /* Device selection (default: LOCAL_RANK mod device count, chosen in
    comm_world).  Must be called before the first comm_world/comm_init.      */
 void exags_set_device(int device);
@@ -40,7 +55,9 @@ unsigned long long exags_kernel_launches(void);
 /* Handle geometry: what[0]=n, [1]=groups G, [2]=member indices S,
    [3]=flagged primaries, [4]=neighbour ranks, [5]=send slots, [6]=recv slots,
    [7]=total_shared (low 32 bits), [8]=method in use, [9]=touched 32B sectors
-   of a double field (low 32 bits), [10]=boundary groups, [11]=interior groups */
+   of a double field, [10]=boundary groups, [11]=interior groups held in CSR
+   form, [12]=their member indices, [13]=flagged primaries heading no group,
+   [14]=handle bytes, [15]=entries of the sliced-ELL index array              */
 void exags_gs_info(const struct gs_data *gsh, unsigned long long what[16]);
 /* Write local map `which` (0 = unflagged members only, 1 = all members,
    2 = flagged primaries, 3 = pairwise recv map, 4 = pairwise send map) in the

@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path[:0] = [os.path.join(ROOT, "exaflow-exags-upc_b200"), os.path.join(ROOT, "oracle"), HERE]
 
+import itertools  # noqa: E402
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -62,7 +64,7 @@ def main():
     unique = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     method = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rank, np_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    gpu = what in ("exec", "exech", "exec2")   # exech: host pointers (staged / pipelined path)
+    gpu = what in ("exec", "exech", "exec2", "execw")   # exech: host pointers (staged / pipelined path)
     if not gpu:
         os.environ["EXAGS_HOST_SETUP_ONLY"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=np_)
@@ -105,7 +107,6 @@ def main():
                     ok = False
     elif what in ("exec", "exech"):
         onhost = what == "exech"
-        import itertools
         # the maps of a handle built on the device (topology, interior/boundary
         # split) against the oracle's, like the CPU-only "setup" mode
         dumps = gather_arrays([g.dump_map(w) for w in range(5)], np_)
@@ -149,6 +150,89 @@ def main():
                         bad = np.flatnonzero(gg.ravel() != w.ravel())
                         print(f"MISMATCH exec case={case} {dname} {op} t={t} mode={mode} rank={r}: "
                               f"{bad.size} of {w.size} differ, first at {bad[:5]}")
+                        ok = False
+    elif what == "comm":
+        # the communicator's collectives on host vectors (src/comm.upc:427-459,706-984):
+        # every rank folds the ranks' vectors in rank order, so even FP sums are the
+        # sequential left-to-right ones; small vectors travel through the control
+        # segment, large ones through published blocks
+        NPOP = {"add": np.add, "mul": np.multiply, "min": np.minimum, "max": np.maximum}
+        for (dname, dt), op, vn in itertools.product(cases.DTYPES.items(), cases.OPS, (1, 5, 70001)):
+            opi, dom = cases.OPS.index(op), X.NP_DOM[np.dtype(dt)]
+            v = cases.values(vn, dt, op, 17 * rank + vn)
+            alls = gather_arrays(v, np_)
+            tot = alls[0].copy()
+            for a in alls[1:]:
+                tot = NPOP[op](tot, a)
+            got = v.copy()
+            X.comm_allreduce(got, dom, opi)
+            if not np.array_equal(got, tot):
+                print(f"MISMATCH comm_allreduce {dname} {op} vn={vn} rank={rank}"); ok = False
+            if vn <= 5:
+                excl, total = X.comm_scan(v, dom, opi)
+                ident = {"add": 0, "mul": 1, "min": np.finfo(dt).max if np.dtype(dt).kind == "f" else np.iinfo(dt).max,
+                         "max": -np.finfo(dt).max if np.dtype(dt).kind == "f" else np.iinfo(dt).min}[op]
+                want = np.full(vn, ident, dtype=dt)
+                for a in alls[:rank]:
+                    want = NPOP[op](want, a)
+                tot_i = np.full(vn, ident, dtype=dt)
+                for a in alls:
+                    tot_i = NPOP[op](tot_i, a)
+                if not (np.array_equal(excl, want) and np.array_equal(total, tot_i)):
+                    print(f"MISMATCH comm_scan {dname} {op} vn={vn} rank={rank}: {excl} {total} vs {want} {tot_i}"); ok = False
+        rng = np.random.default_rng(3 + rank)
+        a, b = rng.uniform(-1, 1, 1001), rng.uniform(-1, 1, 1001)
+        local = 0.0
+        for x, y in zip(a, b):
+            local += x * y                                   # the reference's serial loop (src/tensor.c:12-17)
+        parts = gather_arrays(local, np_)
+        want = parts[0]
+        for x in parts[1:]:
+            want += x
+        if X.comm_dot(a, b) != want:
+            print(f"MISMATCH comm_dot rank={rank}"); ok = False
+        for root in range(np_):
+            buf = np.arange(40, dtype=np.int64) * (rank + 1) + root
+            X.comm_bcast(buf, root)
+            if not np.array_equal(buf, np.arange(40, dtype=np.int64) * (root + 1) + root):
+                print(f"MISMATCH comm_bcast root={root} rank={rank}"); ok = False
+        L = X.lib()
+        import ctypes as C
+        L.exags_comm_reduce__double.restype = C.c_double
+        L.exags_comm_reduce__double.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint]
+        got = L.exags_comm_reduce__double(C.cast(X.comm_world(), C.c_void_p), X.gs_max, a.ctypes.data, a.size)
+        if got != max(gather_arrays(float(a.max()), np_)):
+            print(f"MISMATCH comm_reduce_double rank={rank}"); ok = False
+        okt = torch.tensor([1 if ok else 0]); dist.all_reduce(okt, op=dist.ReduceOp.MIN); ok = bool(okt.item())
+    elif what == "execw":
+        # weighted gs (include/exags_cuda.h): equals gs followed by u[i] *= w[i] on
+        # every DOF whose label is shared with another DOF on any rank
+        labs = np.abs(np.concatenate(all_ids))
+        uniq, cnt = np.unique(labs[labs != 0], return_counts=True)
+        shared = np.isin(np.abs(ids), uniq[cnt >= 2])
+        for dt, op in itertools.product((np.float64, np.float32), cases.OPS):
+            opi, dom = cases.OPS.index(op), X.NP_DOM[np.dtype(dt)]
+            u = cases.values(ids.size, dt, op, 1000 * rank + 3)
+            wts = np.random.default_rng(50 + rank).uniform(0.25, 1.0, ids.size).astype(dt)
+            dev, dw = torch.from_numpy(u.copy()).cuda(), torch.from_numpy(wts).cuda()
+            X.gs_weighted(dev, dw, dom, opi, g)
+            ins, outs = gather_arrays(u, np_), gather_arrays(dev.cpu().numpy(), np_)
+            ws, shs = gather_arrays(wts, np_), gather_arrays(shared, np_)
+            if rank == 0:
+                want = [a.copy() for a in ins]
+                orc.exec(want, 0, 1, O.NP_DOM[np.dtype(dt)], opi, 0)
+                for r in range(np_):
+                    with np.errstate(over="ignore"):
+                        w_r = np.where(shs[r], want[r] * ws[r], want[r]).astype(dt)
+                    exact = np.array_equal(outs[r], w_r)
+                    if not exact and op in ("add", "mul") and method in (0, 3):
+                        try:
+                            np.testing.assert_array_max_ulp(outs[r], w_r, maxulp=4); exact = True
+                        except AssertionError:
+                            pass
+                    if not exact:
+                        bad = np.flatnonzero(outs[r] != w_r)
+                        print(f"MISMATCH execw case={case} {np.dtype(dt).name} {op} rank={r}: {bad.size} differ, first {bad[:5]}")
                         ok = False
     elif what == "exec2":
         # two live handles with different neighbour sets, calls interleaved
@@ -196,6 +280,13 @@ def main():
             if not np.array_equal(dv.cpu().numpy(), np.max(np.stack(alls), axis=0)):
                 print(f"MISMATCH device comm_allreduce n={n_el} rank={rank}")
                 ok = False
+        cnt = np.array([3 + rank, 10 * rank], dtype=np.int64)       # comm_scan: device input and output
+        dout = torch.zeros(4, dtype=torch.int64, device="cuda")
+        X.comm_scan(torch.from_numpy(cnt).cuda(), X.gs_long, X.gs_add, out=dout)
+        allc = np.stack(gather_arrays(cnt, np_))
+        if not np.array_equal(dout.cpu().numpy(), np.concatenate([allc[:rank].sum(axis=0), allc.sum(axis=0)])):
+            print(f"MISMATCH device comm_scan rank={rank}: {dout.cpu().numpy()}")
+            ok = False
         okt = torch.tensor([1 if ok else 0]); dist.all_reduce(okt, op=dist.ReduceOp.MIN); ok = bool(okt.item())
     flag = torch.tensor([0 if ok else 1])
     dist.broadcast(flag, 0)

@@ -428,3 +428,71 @@ def test_comm_dot_device_vectors(X):
     got, want = X.comm_dot(_dev(v), _dev(w)), float(np.dot(v, w))
     scale = float(np.dot(np.abs(v), np.abs(w)))
     assert abs(got - want) <= 64 * np.finfo(np.float64).eps * scale
+
+
+def _shared_mask(ids):
+    """DOFs whose label is shared with another DOF (members of a group)."""
+    labs = np.abs(ids)
+    uniq, cnt = np.unique(labs[labs != 0], return_counts=True)
+    return np.isin(labs, uniq[cnt >= 2])
+
+
+@pytest.mark.parametrize("kind", ["sem", "random_flagged", "long_groups"])
+def test_weighted_gs(X, O, kind):
+    """exags_gs_weighted (include/exags_cuda.h): Nek's dssum followed by the
+    multiplication with an inverse-multiplicity weight, fused into the one pass.
+    Equal, bit for bit, to gs followed by u[i] *= w[i] on every member of a group
+    (one rounding per product either way); other DOFs untouched.  Sliced kernel
+    without and with the flag mask, and the CSR kernel of long groups."""
+    if kind == "sem":
+        ids = semmesh.box_ids(6, 5, 4, 5)
+    elif kind == "random_flagged":
+        ids = cases.random_ids(20000, 6000, 21)
+    else:
+        ids = cases.random_ids(9000, 400, 22, p_flag=0.0, long_group=60)
+    n = ids.size
+    shared = _shared_mask(ids)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    for dt, op in itertools.product((np.float64, np.float32), cases.OPS):
+        opi = cases.OPS.index(op)
+        u = cases.values(n, dt, op, 31)
+        w = np.random.default_rng(8).uniform(0.25, 1.0, n).astype(dt)
+        want = u.copy()
+        o.exec([want], O.M_PLAIN, 1, O.NP_DOM[np.dtype(dt)], opi, 0)
+        with np.errstate(over="ignore"):
+            want = np.where(shared, want * w, want).astype(dt)
+        d, dw = _dev(u), _dev(w)
+        X.gs_weighted(d, dw, X.NP_DOM[np.dtype(dt)], opi, g)
+        assert np.array_equal(d.cpu().numpy(), want), (kind, dt, op)
+        # stream-ordered form on torch's current stream
+        d2 = _dev(u)
+        X.gs_weighted(d2, dw, X.NP_DOM[np.dtype(dt)], opi, g, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d2.cpu().numpy(), want), (kind, dt, op, "async")
+    X.gs_free(g)
+
+
+def test_weighted_gs_is_dsavg(X):
+    """With w = 1 / multiplicity the weighted sum is the average over the copies
+    of a node: a field that is already continuous is reproduced exactly."""
+    dims = (8, 8, 6, 7)
+    ids = semmesh.box_ids(*dims)
+    g = X.gs_setup(ids)
+    m = torch.ones(ids.size, dtype=torch.float64, device="cuda")
+    X.gs(m, X.gs_double, X.gs_add, 0, g)
+    w = 1.0 / m                                            # multiplicities are 1, 2, 4, 8: exact
+    cont = torch.from_numpy(((ids * 2654435761) % 1024).astype(np.float64)).cuda()   # a function of the node
+    u = cont.clone()
+    X.gs_weighted(u, w, X.gs_double, X.gs_add, g)
+    assert torch.equal(u, cont)
+    X.gs_free(g)
+
+
+def test_comm_scan_device_vectors(X):
+    """comm_scan with device input and output (one rank: empty prefix, own total)."""
+    v = torch.tensor([5, -2, 9], dtype=torch.int64, device="cuda")
+    out = torch.zeros(6, dtype=torch.int64, device="cuda")
+    X.comm_scan(v, X.gs_long, X.gs_add, out=out)
+    assert out.cpu().tolist() == [0, 0, 0, 5, -2, 9]
+    excl, tot = X.comm_scan(np.array([2.5, 4.0]), X.gs_double, X.gs_max)
+    assert excl.tolist() == [-np.finfo(np.float64).max] * 2 and tot.tolist() == [2.5, 4.0]

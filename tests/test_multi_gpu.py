@@ -117,3 +117,24 @@ def test_two_handles_interleaved(built):
         pytest.skip(f"needs 4 GPUs, have {_ndev()}")
     codes, outs = run_ranks(4, ["blocks", "exec2", 0, 1], timeout=600)
     assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case,method,transport", [(2, "slab", 1, "ipc"), (3, "random", 1, "push"),
+                                                        (4, "blocks", 1, "push"), (2, "slab", 3, "ipc")])
+def test_weighted_gs_one_gpu(built, np_, case, method, transport):
+    """exags_gs_weighted with np > 1 (ranks sharing GPU 0): interior groups by the
+    weighted sliced / CSR kernels, boundary groups by the weighted unpack, on
+    symmetric (slab, blocks) and flagged (random) maps, pairwise and all-reduce."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, [case, "execw", 0, method], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": transport})
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
+def test_weighted_gs_multi_gpu(built, np_, case):
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "execw", 0, 1], timeout=600)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)

@@ -81,3 +81,13 @@ def test_multirank_setup_unique(built, np_, case):
 def test_multirank_gs_unique(built, np_, case):
     codes, outs = run_ranks(np_, [case, "unique"])
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_", [2, 3, 5])
+def test_multirank_comm_collectives(built, np_):
+    """comm_allreduce (every dom x op; vectors small enough for the control
+    segment and large enough for published blocks), comm_scan, comm_dot,
+    comm_bcast and comm_reduce on host vectors across ranks
+    (src/comm.upc:427-459,706-984): folded in rank order on every rank."""
+    codes, outs = run_ranks(np_, ["fixture", "comm"])
+    assert all(c == 0 for c in codes), "\n".join(outs)
