@@ -496,3 +496,29 @@ def test_comm_scan_device_vectors(X):
     assert out.cpu().tolist() == [0, 0, 0, 5, -2, 9]
     excl, tot = X.comm_scan(np.array([2.5, 4.0]), X.gs_double, X.gs_max)
     assert excl.tolist() == [-np.finfo(np.float64).max] * 2 and tot.tolist() == [2.5, 4.0]
+
+
+def test_gs_async_under_cuda_graph(X, O):
+    """exags_gs_async with one rank makes no host synchronisation and no
+    allocation: a launch-bound inner loop of small gs calls can be captured in a
+    CUDA graph and replayed (the captured kernels read the same device map)."""
+    ids = semmesh.box_ids(4, 4, 3, 5)
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    u0 = cases.values(ids.size, np.float64, "add", 4)
+    want = u0.copy()
+    for _ in range(3):
+        o.exec([want], O.M_PLAIN, 1, O.D_DOUBLE, O.O_ADD, 0)
+    u = _dev(u0)
+    X.gs(u, X.gs_double, X.gs_add, 0, g)          # warm-up outside the capture (module load)
+    u.copy_(torch.from_numpy(u0))
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            X.gs_async(u, X.mode_plain, 1, X.gs_double, X.gs_add, 0, g, s)
+    u.copy_(torch.from_numpy(u0))                 # capture does not execute; replay does
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(u.cpu().numpy(), want)
+    X.gs_free(g)
