@@ -91,6 +91,9 @@ def main():
                     if not np.array_equal(dumps[r][w], want):
                         print(f"MISMATCH case={case} rank={r} map={w}\n got {dumps[r][w][:40]}\n want {want[:40]}")
                         ok = False
+                if method == 2 and infos[r]["method"] != X.gs_pairwise:
+                    print(f"MISMATCH crystal-router request kept method {infos[r]['method']} on rank {r}")
+                    ok = False
                 if infos[r]["total_shared"] != orc.total_shared:
                     print(f"MISMATCH total_shared rank={r}: {infos[r]['total_shared']} vs {orc.total_shared}")
                     ok = False

@@ -48,7 +48,7 @@ def test_multirank_exec_unique(built, np_, case):
 
 @pytest.mark.parametrize("np_,case,method,unique", [(2, "slab", 1, 0), (3, "random", 1, 0), (4, "blocks", 1, 0),
                                                     (2, "fixture", 3, 0), (4, "blocks", 3, 0), (2, "slab", 1, 1),
-                                                    (2, "empty", 1, 0)])
+                                                    (2, "empty", 1, 0), (2, "fixture", 2, 0)])
 def test_multirank_exec_one_gpu(built, np_, case, method, unique):
     """np ranks as processes sharing GPU 0: the library detects the shared
     device and exchanges halos with CUDA-IPC pulls instead of NCCL, so the

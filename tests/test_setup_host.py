@@ -91,3 +91,11 @@ def test_multirank_comm_collectives(built, np_):
     (src/comm.upc:427-459,706-984): folded in rank order on every rank."""
     codes, outs = run_ranks(np_, ["fixture", "comm"])
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks")])
+def test_multirank_setup_crystal_router_request(built, np_, case):
+    """gs_crystal_router requests (src/gs.h:127) run the direct pairwise
+    exchange: the handle must carry the pairwise maps."""
+    codes, outs = run_ranks(np_, [case, "setup", 0, 2])
+    assert all(c == 0 for c in codes), "\n".join(outs)
