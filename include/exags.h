@@ -348,6 +348,12 @@ void fgslib_gs_free_(const int *handle);
 # define gs_scatter_many_to_vec exags_gs_scatter_many_to_vec
 # define gs_scatter_vec_to_many exags_gs_scatter_vec_to_many
 # ifndef EXAGS_NO_INT_MACROS
+/* glibc's <sys/types.h> has its own `uint` and `ulong` typedefs: take it in
+   before the names become macros, so that a system header included after this
+   one cannot re-declare them through the macros (the reference's types.h has
+   the same hazard and relies on callers including system headers first) */
+#  include <sys/types.h>
+#  include <stdlib.h>
 #  define sint  exags_sint
 #  define uint  exags_uint
 #  define slong exags_slong

@@ -125,3 +125,64 @@ int caller(void) {
         r = subprocess.run(["gcc", "-std=gnu99", "-c", str(src), "-I", os.path.join(ROOT, "include"),
                             "-o", str(tmp_path / "caller.o")] + flags, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_install_layout_and_pkg_config(built, tmp_path):
+    """`make install` lays out what the reference's does (src/Makefile.am:1-14,
+    exags.pc.in): libexags, the headers under include/exags/, exags.pc.  A caller
+    that uses the call patterns of the reference's in-tree users of gs
+    (src/xxt.upc:619-631, src/amg.upc:94-109,200,215,266,403,468,543-545) builds
+    and links from `pkg-config --cflags --libs exags` alone, in both flavours."""
+    import shutil
+    import subprocess
+    if not shutil.which("pkg-config"):
+        pytest.skip("pkg-config not installed")
+    src = tmp_path / "intree_callers.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include "exags/c99.h"
+#include "exags/name.h"
+#include "exags/fail.h"
+#include "exags/types.h"
+#include "exags/comm.h"
+#include "exags/mem.h"
+#include "exags/gs_defs.h"
+#include "exags/gs.h"
+struct rid { sint p, i; };
+int main(void) {
+  comm_ptr world, comm; struct gs_data *gsh, *top; buffer buf = null_buffer;
+  comm_init(); comm_world(&world); comm_dup(&comm, world);
+  { ulong bid[4] = {3, 3, 5, 0}; sint v[4] = {6, 7, 1, 0};           /* xxt.upc:619-631 */
+    gsh = gs_setup((const slong *)bid, 4, comm, 0, gs_pairwise, 0);
+    gs(v, gs_sint, gs_bpr, 0, gsh, &buf);
+    gs(v, gs_sint, gs_add, 0, gsh, &buf);
+    gs_free(gsh); }
+  { slong id[3] = {1, 1, 2}; double x[3] = {1, 2, 3}, avg[4] = {0}; struct rid rid[3] = {{0, 0}, {0, 1}, {0, 2}};
+    int dump = 0, not_happy = 0; uint n = 3;
+    comm_bcast(comm, &dump, sizeof(int), 0);                         /* amg.upc:543 */
+    top = gs_setup((const slong *)id, n, comm, 1, gs_auto, 1);       /* amg.upc:545, 403 */
+    gs(x, gs_double, gs_add, 1, top, 0);                             /* amg.upc:109,194 */
+    gs(x, gs_double, gs_add, 0, top, 0);                             /* amg.upc:94,205 */
+    avg[0] = comm_reduce_double(comm, gs_add, x, n);                 /* amg.upc:200 */
+    comm_allreduce(comm, gs_double, gs_add, avg, 2, avg + 2);        /* amg.upc:215 */
+    gs_vec(n ? &rid[0].p : 0, 2, gs_sint, gs_add, 0, top, &buf);     /* amg.upc:266 */
+    if (comm_reduce_int(comm, gs_max, &not_happy, 1)) comm_barrier(comm);   /* amg.upc:468 */
+    gs_free(top); }
+  buffer_free(&buf); comm_free(&comm); comm_free(&world);
+  return 0;
+}''')
+    for nek in ("", "1"):
+        prefix = tmp_path / ("inst_nek" if nek else "inst")
+        r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "exaflow-exags-upc_b200"), "install",
+                            f"PREFIX={prefix}"] + (["NEK=1"] if nek else []), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        for rel in ("lib/libexags.so", "lib/pkgconfig/exags.pc", "include/exags.h", "include/exags/gs.h",
+                    "include/exags/comm.h", "include/exags/mem.h", "include/exags/types.h"):
+            assert (prefix / rel).exists(), rel
+        env = dict(os.environ, PKG_CONFIG_PATH=str(prefix / "lib" / "pkgconfig"))
+        flags = subprocess.run(["pkg-config", "--cflags", "--libs", "exags"], capture_output=True, text=True, env=env)
+        assert flags.returncode == 0, flags.stderr
+        assert ("-DGLOBAL_LONG_LONG" in flags.stdout) == bool(nek)
+        r = subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", str(src), "-o", str(tmp_path / "intree")]
+                           + flags.stdout.split(), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
