@@ -186,3 +186,28 @@ int main(void) {
         r = subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", str(src), "-o", str(tmp_path / "intree")]
                            + flags.stdout.split(), capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_product_does_not_touch_the_oracle(built):
+    """The oracle is test infrastructure: no source of the product names it, the
+    built library neither links it nor carries a CPU reduction path by its name,
+    and loading the product does not load it."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "exaflow-exags-upc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".c", ".cu", ".h", ".py", ".map")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+    lib = os.path.join(pkg, "exags_b200", "libexags.so")
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    assert "gs_oracle" not in needed and "exags_ref" not in needed
+    code = ("import sys; sys.path.insert(0, %r); import exags_b200 as X; X.lib(); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'libgs_oracle' not in maps and 'libexags_ref' not in maps; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % pkg)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
