@@ -119,7 +119,11 @@ static void make_key(struct xg_world *w)
     fclose(f);
   }
   const char *port = getenv("MASTER_PORT");
-  snprintf(w->key, sizeof w->key, "%d-%llu-%s", (int)getppid(), start, port ? port : "0");
+  /* an elastic launcher restarts its workers under the same agent: the restart
+     count keeps a new attempt off the segment a failed one may have left */
+  const char *attempt = getenv("TORCHELASTIC_RESTART_COUNT");
+  snprintf(w->key, sizeof w->key, "%d-%llu-%.8s-%.4s", (int)getppid(), start, port ? port : "0",
+           attempt ? attempt : "0");
 }
 
 static void ctl_name(const struct xg_world *w, char *out, size_t cap)
