@@ -15,7 +15,8 @@ DT = [np.float64, np.float32, np.int32, np.int64]
 
 
 @pytest.mark.parametrize("np_,unique,method,seed", [(1, 0, 1, 0), (1, 1, 1, 1), (2, 0, 1, 2), (2, 0, 3, 3),
-                                                    (4, 0, 1, 4), (4, 1, 1, 5), (2, 1, 3, 6)])
+                                                    (4, 0, 1, 4), (4, 1, 1, 5), (2, 1, 3, 6),
+                                                    (8, 0, 1, 7), (8, 0, 3, 8), (8, 1, 1, 9)])
 def test_oracle_matches_reference(O, np_, unique, method, seed):
     ids = [cases.random_ids(260 + 13 * r, 70, 1000 * seed + r, p_flag=0.0 if unique else 0.25) for r in range(np_)]
     combos = [(1, 8, 0, 0, 0)] + [(m, vn, d, o, t) for (m, vn), (d, o), t in
