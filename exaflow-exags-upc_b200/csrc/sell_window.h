@@ -55,7 +55,11 @@ XG_HD static inline u32 xg_sell_width(u32 size) { return size <= 2 ? 2u : size <
    width class (EXAGS_SELL_PAIRS, for A/B runs).
    ord[t] = position (k - first) of the t-th group to deal, ph[t] its phase;
    returns the number of groups of the class.  Lines are taken as 16 elements (128 bytes of
-   doubles; for 4-byte fields that is half a line, which still shares).      */
+   doubles; for 4-byte fields that is half a line, which still shares).  Bits
+   8.. of `chain` may carry another line size as a shift (5: 32 elements, the
+   line of a 4-byte field; EXAGS_SELL_LINE_SHIFT, an experiment knob): a unit
+   then takes up to 2^(shift-3) - 1 twins, which for doubles is the same set of
+   lines per instruction (rows r..r+3 are two full lines either way).          */
 XG_HD static inline u32 xg_sell_class_order(u32 first, u32 last, const u32 *sg, const u32 *off,
                                             const u32 *idx, u32 wd, unsigned short *ord,
                                             unsigned char *ph, int chain)
@@ -70,6 +74,9 @@ XG_HD static inline u32 xg_sell_class_order(u32 first, u32 last, const u32 *sg, 
     if (M == XG_SELL_WSLOTS / 2) break;           /* cannot happen: >= 2 slots each */
     ck[M] = (unsigned short)(k - first); P[M] = idx[a]; Q[M] = idx[a + 1]; ++M;
   }
+  const unsigned ls = (chain >> 8) ? (unsigned)(chain >> 8) : 4u;
+  const u32 max_twins = (1u << (ls - 3u)) - 1u;
+  chain &= 0xff;
   if (!chain || (chain == 1 && wd != 2)) {        /* plain primary order, no phases */
     for (u32 s = 0; s < M; ++s) { ord[s] = ck[s]; ph[s] = 0; }
     return M;
@@ -83,17 +90,18 @@ XG_HD static inline u32 xg_sell_class_order(u32 first, u32 last, const u32 *sg, 
     unsigned char phase = 0;
     for (;;) {
       XG_MARK(cur); ord[ne] = ck[cur]; ph[ne] = phase; ++ne;
-      const u32 tw = cur + 1;                      /* twin: the next pair in primary order */
-      if (tw < M && !XG_USED(tw) && (P[tw] >> 4) == (P[cur] >> 4) && (Q[tw] >> 4) == (Q[cur] >> 4)) {
+      /* twins: the next pairs in primary order that share both lines */
+      for (u32 tw = cur + 1; tw < M && tw <= cur + max_twins; ++tw) {
+        if (XG_USED(tw) || (P[tw] >> ls) != (P[cur] >> ls) || (Q[tw] >> ls) != (Q[cur] >> ls)) break;
         XG_MARK(tw); ord[ne] = ck[tw]; ph[ne] = phase; ++ne;
       }
       /* successor: first unused pair whose primary lies in the partner's line
          (P ascends: binary search for the start of the line) */
-      const u32 line = Q[cur] >> 4;
+      const u32 line = Q[cur] >> ls;
       u32 lo = 0, hi = M;
-      while (lo < hi) { const u32 mid = lo + (hi - lo) / 2; if ((P[mid] >> 4) < line) lo = mid + 1; else hi = mid; }
-      while (lo < M && (P[lo] >> 4) == line && XG_USED(lo)) ++lo;
-      if (lo < M && (P[lo] >> 4) == line) { cur = lo; phase ^= 1; } else break;
+      while (lo < hi) { const u32 mid = lo + (hi - lo) / 2; if ((P[mid] >> ls) < line) lo = mid + 1; else hi = mid; }
+      while (lo < M && (P[lo] >> ls) == line && XG_USED(lo)) ++lo;
+      if (lo < M && (P[lo] >> ls) == line) { cur = lo; phase ^= 1; } else break;
     }
   }
 #undef XG_USED

@@ -256,7 +256,11 @@ int xg_sell_pairs_enabled(void)
 {
   const char *e = getenv("EXAGS_SELL_PAIRS");
   const int v = e ? atoi(e) : 2;
-  return v < 0 ? 0 : v > 2 ? 2 : v;
+  /* EXAGS_SELL_LINE_SHIFT (4..6, default 4 = 16 elements): line size the
+     ordering works with, in bits 8.. of the value (sell_window.h)           */
+  const char *l = getenv("EXAGS_SELL_LINE_SHIFT");
+  const int ls = l ? atoi(l) : 4;
+  return (v < 0 ? 0 : v > 2 ? 2 : v) | ((ls >= 4 && ls <= 6 && ls != 4) ? ls << 8 : 0);
 }
 
 void xg_sell_build(struct xg_sell *s, const struct xg_hmap *m)

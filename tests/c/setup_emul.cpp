@@ -153,6 +153,8 @@ extern "C" unsigned long long setup_emul_line_visits(const void *id, int idbytes
   xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
   xg_sell hs; xg_sell_build(&hs, &hh);
   unsigned long long visits = 0;
+  const char *lsenv = getenv("EXAGS_EMUL_LINE_SHIFT");        // 4: doubles (default), 5: 4-byte fields
+  const unsigned lshift = lsenv ? (unsigned)atoi(lsenv) : 4u;
   for (u32 b = 0; b < hs.nblock; ++b)
     for (int j = 0; j < 8; ++j) {
       u32 lines[32]; int nl = 0;
@@ -162,7 +164,7 @@ extern "C" unsigned long long setup_emul_line_visits(const void *id, int idbytes
         const int slot = ((ph >> ((j | 1))) & 1u) ? (j ^ 1) : j;
         const u32 v = hs.idx[L * 8 + slot];
         if (v == XG_NONE) continue;
-        const u32 line = v >> 4;
+        const u32 line = v >> lshift;
         bool seen = false;
         for (int q = 0; q < nl; ++q) if (lines[q] == line) { seen = true; break; }
         if (!seen) lines[nl++] = line;
