@@ -47,6 +47,13 @@ def make_ids(case, np_, rank):
         own = base + np.arange(1, 3001, dtype=np.int64)
         nxt = 10**6 * (rank + 1) + np.arange(1, 41, dtype=np.int64)      # shared with rank+1
         return np.concatenate([own, nxt, own[:500]])
+    if case.startswith("fuzz"):   # fuzz<seed>: sizes, label density, zeros and flags drawn from the seed
+        seed = int(case[4:])
+        rng = np.random.default_rng(1000 + seed)
+        nlabels = int(rng.integers(5, 400))
+        n = int(rng.integers(0, 900)) if rng.random() < 0.9 else 0
+        return cases.random_ids(n + 17 * rank, nlabels, 7919 * seed + rank, p_zero=float(rng.choice([0.0, 0.1, 0.5])),
+                                p_flag=float(rng.choice([0.0, 0.25, 0.9])), long_group=int(rng.choice([0, 0, 30])))
     if case == "empty":      # rank 1 owns nothing
         return cases.random_ids(0 if rank == 1 else 200, 80, 5 + rank)
     raise SystemExit(f"unknown case {case}")
@@ -74,6 +81,8 @@ def main():
         ndev = torch.cuda.device_count()
         X.lib().exags_set_device(rank % ndev)
     ids = make_ids(case, np_, rank)
+    if unique and case.startswith("fuzz"):
+        ids = np.abs(ids)     # unique on pre-flagged labels is the reference quirk of DESIGN.md 2, not compared
     g = X.gs_setup(ids, unique=unique, method=method)
     info = g.info()
     all_ids = gather_arrays(ids, np_)

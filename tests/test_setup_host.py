@@ -99,3 +99,13 @@ def test_multirank_setup_crystal_router_request(built, np_, case):
     exchange: the handle must carry the pairwise maps."""
     codes, outs = run_ranks(np_, [case, "setup", 0, 2])
     assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,seed", [(2, 1), (3, 2), (4, 3), (7, 6)])
+def test_multirank_setup_fuzz(built, np_, seed):
+    """Randomised label sets (sizes, density, zeros, flags, a long group drawn
+    from the seed): all five maps of every rank against the oracle, with and
+    without unique."""
+    for unique in (0, 1):
+        codes, outs = run_ranks(np_, [f"fuzz{seed}", "setup", unique])
+        assert all(c == 0 for c in codes), "\n".join(outs)
