@@ -294,3 +294,23 @@ done:
   xg_sell_free(&hs); xg_hmap_free(&hh); free(hfp); free(hfs); xg_topo_free(&ht);
   return out;
 }
+
+// The sliced layout itself, for layout studies in Python: returns the number of
+// blocks; idx_out (cap_blocks * 256 uints) and mask_out (cap_blocks * 32 bytes)
+// are filled when they are large enough.
+extern "C" size_t setup_emul_sell_dump(const void *id, int idbytes, size_t n, u32 *idx_out,
+                                       unsigned char *mask_out, size_t cap_blocks)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht; xg_topo_build(&ht, wide.data(), n);
+  xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
+  xg_sell hs; xg_sell_build(&hs, &hh);
+  const size_t nb = hs.nblock;
+  if (nb <= cap_blocks && idx_out && mask_out) {
+    memcpy(idx_out, hs.idx, nb * 256 * sizeof(u32));
+    memcpy(mask_out, hs.mask, nb * 32);
+  }
+  xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
+  return nb;
+}
