@@ -238,6 +238,18 @@ struct xcu_sell {
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose);
+/* device SELL map with the compressed index stream (sell_window.h: 16-bit
+   codes, per-window base + dictionary); experiment, EXAGS_SELL_COMPRESS=1    */
+struct xcu_csell {
+  u32 nblock;
+  const unsigned char *mask;      /* the start / phase masks of the raw map  */
+  const unsigned short *code;     /* [nblock*256]                             */
+  const u32 *hdr;                 /* [nwin*2] base, dictionary entries        */
+  const u32 *dict;                /* [nwin*256]                               */
+};
+/* plain fields (one component), maps without flagged members */
+void xcu_fused_sell_c(void *stream, const struct xcu_csell *m, const struct xcu_field *f,
+                      int xdom, int xop);
 void xcu_gather_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                      int mode, int xdom, int xop);
 

@@ -375,6 +375,38 @@ k_fused_w(xcu_csr m, T *__restrict__ u, const T *__restrict__ wgt, int transpose
   for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
 }
 
+// Compressed index stream (experiment, EXAGS_SELL_COMPRESS=1; format in
+// sell_window.h): the lane's 8 member indices arrive as 8 16-bit codes (one
+// 128-bit load instead of two) and are rebuilt from the window's base and its
+// small dictionary of member-to-primary distances, held in shared memory; the
+// rest is sell_lane as in k_fused_sell.  One CTA is one window.
+template <typename T, int OP, int MINB>
+__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+k_fused_sell_c(xcu_csell m, Fld<T, XM_PLAIN> f)
+{
+  static_assert(XG_SELL_CW == XG_SELL_WB, "compressed windows: one CTA per window");
+  __shared__ u32 dict[256];
+  const u32 w = blockIdx.x;
+  const u32 base = __ldg(m.hdr + 2u * w), nd = __ldg(m.hdr + 2u * w + 1u);
+  for (u32 t = threadIdx.x; t < nd; t += 32u * XG_SELL_CW) dict[t] = __ldg(m.dict + (size_t)w * 256u + t);
+  __syncthreads();
+  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.code + ((size_t)c * 32u + lane) * 8u));
+  const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
+  const unsigned start = startph & 0x55u;
+  const u32 h[8] = { raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16,
+                     raw.z & 0xFFFFu, raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16 };
+  u32 id[8], prim = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if ((start >> j) & 1u) { prim = base + h[j]; id[j] = prim; }
+    else id[j] = (h[j] == 0xFFFFu) ? XG_NONE : prim + dict[h[j] & 255u];
+  }
+  const uint4 a = make_uint4(id[0], id[1], id[2], id[3]), b = make_uint4(id[4], id[5], id[6], id[7]);
+  sell_lane<T, OP, XM_PLAIN, 1>(f, a, b, startph);
+}
+
 // gs_vec with 3-tuples (a velocity field, BASELINE config 3): a tuple is 3
 // consecutive elements, so its address is aligned to one element only.  Read
 // it as one aligned pair plus one single -- pair first when the index is even,
@@ -902,6 +934,22 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
     FOR_DOM(XM_MANY, X)
 #undef X
   }
+  LAUNCHED();
+}
+
+void xcu_fused_sell_c(void *stream, const xcu_csell *m, const xcu_field *f, int xdom, int xop)
+{
+  if (!m->nblock) return;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = m->nblock / XG_SELL_CW;
+  const unsigned nthr = 32 * XG_SELL_CW;
+  xcu_field f1 = *f;
+  f1.vn = 1; f1.tuple = 1;
+  const int mode = XM_PLAIN;
+#define X(T, OP, MODE)                                                        \
+  k_fused_sell_c<T, OP, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
+  FOR_ALL(X)
+#undef X
   LAUNCHED();
 }
 

@@ -20,6 +20,7 @@
 #include <string.h>
 #include "exags_internal.h"
 #include "gs_plan.h"
+#include "sell_window.h"
 
 struct dev_csr { struct xcu_csr c; u32 *off, *idx, *nunf; };
 
@@ -45,6 +46,9 @@ struct gs_data {
   struct xcu_sell d_sell;     /* interior groups, sliced-ELL form (symmetric maps) */
   void *d_sell_mem[3];
   size_t sell_idx_entries;
+  struct xcu_csell d_csell;   /* the same interior map with the compressed index stream
+                                 (experiment, EXAGS_SELL_COMPRESS=1); nblock 0: not in use */
+  void *d_csell_mem[3];
   /* pipelined host-pointer path (np == 1, symmetric map): chunk schedule */
   u32 nwin, *win_min, *win_max;       /* host copies from the sliced layout */
   u32 *h_bidx; size_t h_nbidx;        /* boundary groups' member indices (np > 1) */
@@ -414,7 +418,9 @@ static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, uns
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
     f.w = wgt;      /* weighted gs: the stores of the group results carry the weight */
-    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
+    if (g->d_csell.nblock && !wgt && (mode == XM_PLAIN || f.vn == 1) && xop <= XO_MAX)
+      xcu_fused_sell_c(stream, &g->d_csell, &f, xd, xop);
+    else if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
     if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
@@ -706,6 +712,45 @@ static int upload_send_primaries(struct gs_data *g, int m)
     free(sp);
   }
   return m;
+}
+
+/* EXAGS_SELL_COMPRESS=1 (experiment): a second copy of the interior map with
+   16-bit codes in place of the 32-bit member indices (sell_window.h).  The
+   windows are encoded on the host from the raw layout -- fetched back when the
+   handle was built on the device -- and the plain one-component calls then run
+   k_fused_sell_c.  Maps with flagged members, or with a window the encoding
+   refuses, stay as they are.                                                 */
+static void compress_interior(struct gs_data *g)
+{
+  const char *e = getenv("EXAGS_SELL_COMPRESS");
+  if (!(e && atoi(e)) || !g->on_device || !g->d_sell.nblock || g->d_sell.fmask) return;
+  const u32 nblock = g->d_sell.nblock, nwin = nblock / XG_SELL_WB;
+  u32 *idx = xnew(u32, (size_t)nblock * 256);
+  unsigned char *mask = xnew(unsigned char, (size_t)nblock * 32);
+  xcu_d2h(idx, g->d_sell.idx, (size_t)nblock * 256 * sizeof(u32), 0);
+  xcu_d2h(mask, g->d_sell.mask, (size_t)nblock * 32, 0);
+  xcu_device_sync();
+  unsigned short *code = xnew(unsigned short, (size_t)nblock * 256);
+  u32 *hdr = xnew0(u32, (size_t)nwin * 2), *dict = xnew0(u32, (size_t)nwin * XG_SELL_CDICT);
+  int refused = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64) num_threads(xg_setup_threads()) reduction(| : refused)
+#endif
+  for (size_t w = 0; w < nwin; ++w)
+    refused |= xg_sell_compress_window(idx + w * XG_SELL_WSLOTS, mask + w * XG_SELL_LANES,
+                                       code + w * XG_SELL_WSLOTS, dict + w * XG_SELL_CDICT, hdr + w * 2);
+  if (!refused) {
+    g->d_csell_mem[0] = upload(code, (size_t)nblock * 256 * sizeof(unsigned short));
+    g->d_csell_mem[1] = upload(hdr, (size_t)nwin * 2 * sizeof(u32));
+    g->d_csell_mem[2] = upload(dict, (size_t)nwin * XG_SELL_CDICT * sizeof(u32));
+    xcu_device_sync();
+    g->d_csell.nblock = nblock;
+    g->d_csell.mask = g->d_sell.mask;
+    g->d_csell.code = (const unsigned short *)g->d_csell_mem[0];
+    g->d_csell.hdr = (const u32 *)g->d_csell_mem[1];
+    g->d_csell.dict = (const u32 *)g->d_csell_mem[2];
+  }
+  free(idx); free(mask); free(code); free(hdr); free(dict);
 }
 
 static void split_groups(struct gs_data *g, const struct xg_topo *t)
@@ -1114,6 +1159,7 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
   }
   if (dev_maps) {
     setup_device_np1(g, id, idbytes, n, prof);
+    compress_interior(g);
     free(id_own); free(id_staged);
     g->method = method == gs_all_reduce ? gs_all_reduce : gs_pairwise;
     if (verbose && comm->id == 0) {
@@ -1168,6 +1214,7 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
            "sector count %.3f s, exchange plan %.3f s, split + sliced layout + upload %.3f s\n", n,
            tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
 #undef TICK
+  compress_interior(g);
   /* the NCCL communicator is created here, collectively, never lazily inside
      a ncclGroupStart/End bracket */
   if (np > 1) xg_plan_exchange_offsets(&g->plan, w);
@@ -1239,6 +1286,7 @@ void exags_gs_free(struct gs_data *g)
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
     xcu_free(g->d_fs);
     for (int m = 0; m < 3; ++m) xcu_free(g->d_sell_mem[m]);
+    for (int m = 0; m < 3; ++m) xcu_free(g->d_csell_mem[m]);
     for (int m = 0; m < 20; ++m) xcu_free(g->d_bnd_mem[m]);
     xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);

@@ -314,3 +314,32 @@ extern "C" size_t setup_emul_sell_dump(const void *id, int idbytes, size_t n, u3
   xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
   return nb;
 }
+
+// Compressed index stream (sell_window.h): every window that the encoder
+// accepts must decode back to its raw slots.  Returns the number of windows
+// that are not compressible, or -1 on a decode mismatch.
+extern "C" long setup_emul_compress_roundtrip(const void *id, int idbytes, size_t n)
+{
+  std::vector<i64> wide(n ? n : 1);
+  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
+  xg_topo ht; xg_topo_build(&ht, wide.data(), n);
+  xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
+  xg_sell hs; xg_sell_build(&hs, &hh);
+  long refused = 0;
+  std::vector<unsigned short> code(XG_SELL_WSLOTS);
+  std::vector<u32> dict(XG_SELL_CDICT);
+  for (u32 w = 0; w < hs.nwin && refused >= 0; ++w) {
+    const u32 *widx = hs.idx + (size_t)w * XG_SELL_WSLOTS;
+    const unsigned char *wmask = hs.mask + (size_t)w * XG_SELL_LANES;
+    u32 hdr[2];
+    if (xg_sell_compress_window(widx, wmask, code.data(), dict.data(), hdr)) { ++refused; continue; }
+    if (hdr[1] > XG_SELL_CDICT) { refused = -1; break; }
+    for (u32 L = 0; L < XG_SELL_LANES; ++L) {
+      u32 out[8];
+      xg_sell_decompress_lane(code.data() + L * 8, wmask[L], dict.data(), hdr[0], out);
+      if (memcmp(out, widx + L * 8, sizeof out)) { refused = -1; break; }
+    }
+  }
+  xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
+  return refused;
+}
