@@ -387,13 +387,18 @@ k_fused_sell_c(xcu_csell m, Fld<T, XM_PLAIN> f)
   static_assert(XG_SELL_CW == XG_SELL_WB, "compressed windows: one CTA per window");
   __shared__ u32 dict[256];
   const u32 w = blockIdx.x;
-  const u32 base = __ldg(m.hdr + 2u * w), nd = __ldg(m.hdr + 2u * w + 1u);
-  for (u32 t = threadIdx.x; t < nd; t += 32u * XG_SELL_CW) dict[t] = __ldg(m.dict + (size_t)w * 256u + t);
-  __syncthreads();
   const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
+  // every load below is independent of the others: one trip to memory, not three.
+  // The first 64 dictionary entries (two lines; a structured mesh uses 7) are
+  // fetched without waiting for the entry count, the rare rest after it.
   const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.code + ((size_t)c * 32u + lane) * 8u));
   const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
+  const uint2 hd = __ldg(reinterpret_cast<const uint2 *>(m.hdr) + w);
+  if (threadIdx.x < 64u) dict[threadIdx.x] = __ldg(m.dict + (size_t)w * 256u + threadIdx.x);
+  const u32 base = hd.x, nd = hd.y;
+  for (u32 t = 64u + threadIdx.x; t < nd; t += 32u * XG_SELL_CW) dict[t] = __ldg(m.dict + (size_t)w * 256u + t);
+  __syncthreads();
   const unsigned start = startph & 0x55u;
   const u32 h[8] = { raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16,
                      raw.z & 0xFFFFu, raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16 };
