@@ -1,5 +1,14 @@
-import sys, numpy as np
-sys.path.insert(0,'/root/repo/tools'); sys.path.insert(0,'/root/repo/exaflow-exags-upc_b200')
+"""Feasibility numbers behind the compressed index stream (csrc/sell_window.h): per window of
+the sliced layout, the span of the primaries and the number of distinct member-to-primary
+distances, for structured boxes and for a box whose elements are numbered in random order.
+Host-side, no GPU.    python tools/compress_study.py"""
+import os
+import sys
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(_ROOT, "tools"), os.path.join(_ROOT, "exaflow-exags-upc_b200")]
 import layout_study as LS
 from exags_b200 import semmesh
 def study(ids, name):

@@ -9,7 +9,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "exaflow-exags-upc_b200")]
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import exags_b200 as X  # noqa: E402
 from exags_b200 import semmesh  # noqa: E402

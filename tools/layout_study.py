@@ -33,7 +33,7 @@ def visits(idx,mask,shift=4):
         f[:,:,j]=np.where(sw,b,a); f[:,:,j+1]=np.where(sw,a,b)
     tot=0; per_slot=[]
     for j in range(8):
-        v=f[:,:,j]; cnt=0
+        v=f[:,:,j]
         lines=np.where(v==NONE,np.uint32(NONE),v>>shift)
         s=np.sort(lines,axis=1)
         distinct=(s[:,1:]!=s[:,:-1]).sum(axis=1)+1
@@ -47,8 +47,6 @@ if __name__=="__main__":
     print("blocks",idx.shape[0],"visits/element",sum(ps)/nel,[round(p/nel,1) for p in ps])
     # lower bound: distinct lines with members per element
     mem=idx[idx!=0xFFFFFFFF]; print("member lines per element", np.unique(mem>>4).size/nel, "members/el", mem.size/nel)
-    # classify lanes by width class via start masks: count groups of size 2,4,8
-    start=mask&0x55
 
 def classes(idx,mask):
     """width class (2,4,8) of every slot, 0 for empty"""
