@@ -179,6 +179,71 @@ def run_reference(args) -> None:
 # --------------------------------------------------------------------------
 #  GPU arm
 # --------------------------------------------------------------------------
+def run_check(X, g, world, n, ids_dev, ints_dev, hbuf, stream, dist) -> dict:
+    """Exact, size-independent checks on the handle that was just timed, at every
+    N (the reference runs its gs test at every thread count,
+    tests/gs/gs_test.upc:118-240): none of them needs the CPU oracle.
+      multiplicity   gs(add,double) of ones gives m in {1,2,4,8} and sum(1/m)
+                     over all ranks is the number of distinct mesh nodes;
+      add_long       gs(add,long) of a partition-independent random field
+                     equals a dense scatter-add by global id (torch), summed
+                     over ranks, gathered back by id -- bit for bit;
+      max_idempotent gs(max,double) twice equals once;
+      host_pointer   the multiplicity check through the blocking gs() on host
+                     memory (the e2e path)."""
+    import torch
+    from exags_b200 import semmesh
+    out = {}
+
+    def allsum(t):
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    unique_nodes = semmesh.box_counts(EX, EY, EZ * world, ORDER)["unique"]
+    m = torch.ones(n, dtype=torch.float64, device="cuda")
+    X.gs_async(m, X.mode_plain, 1, X.gs_double, X.gs_add, 0, g, stream)
+    torch.cuda.synchronize()
+    in_set = bool(((m == 1) | (m == 2) | (m == 4) | (m == 8)).all().item())
+    total = allsum((1.0 / m).sum().reshape(1))          # eighths: exact in double in any order
+    out["multiplicity"] = in_set and float(total.item()) == float(unique_nodes)
+    del m
+
+    nglob = (EX * ORDER + 1) * (EY * ORDER + 1) * (EZ * world * ORDER + 1)
+    dense = torch.zeros(nglob, dtype=torch.int64, device="cuda")
+    dense.scatter_add_(0, ids_dev - 1, ints_dev)
+    allsum(dense)
+    want = dense[ids_dev - 1]
+    del dense
+    got = ints_dev.clone()
+    X.gs_async(got, X.mode_plain, 1, X.gs_long, X.gs_add, 0, g, stream)
+    torch.cuda.synchronize()
+    out["add_long"] = bool(torch.equal(got, want))
+    del got, want
+
+    a = hbuf.cuda()
+    X.gs_async(a, X.mode_plain, 1, X.gs_double, X.gs_max, 0, g, stream)
+    torch.cuda.synchronize()
+    b = a.clone()
+    X.gs_async(b, X.mode_plain, 1, X.gs_double, X.gs_max, 0, g, stream)
+    torch.cuda.synchronize()
+    out["max_idempotent"] = bool(torch.equal(a, b))
+    del a, b
+
+    hbuf.fill_(1.0)
+    X.gs(hbuf.numpy(), X.gs_double, X.gs_add, 0, g)
+    in_set = bool(((hbuf == 1) | (hbuf == 2) | (hbuf == 4) | (hbuf == 8)).all().item())
+    total = allsum((1.0 / hbuf).sum().reshape(1).cuda())
+    out["host_pointer"] = in_set and float(total.item()) == float(unique_nodes)
+
+    flags = torch.tensor([int(bool(v)) for v in out.values()], device="cuda")
+    if dist is not None:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)     # a case passes only if it passed on every rank
+    out = {k: bool(f) for k, f in zip(out, flags.tolist())}
+    return {"ok": all(out.values()), "cases": out, "unique_nodes": unique_nodes,
+            "what": "exact checks on the timed handle, all ranks (see run_check in bench.py)"}
+
+
 def run_gpu(args) -> None:
     import torch
     import exags_b200 as X
@@ -211,9 +276,11 @@ def run_gpu(args) -> None:
     t_setup = time.perf_counter() - t1
     info = g.info()
     transport = X.exchange_transport()
+    ids_dev = torch.from_numpy(ids).cuda()
     del ids
     dof = semmesh.slab_dof_numbers(EX, EY, EZ, ORDER, rank * EZ)
     host = torch.from_numpy(semmesh.field_values(dof, np.float64)).pin_memory()
+    ints_dev = torch.from_numpy(semmesh.field_values(dof, np.int64)).cuda()
     del dof
     u = host.cuda()
     stream = torch.cuda.current_stream().cuda_stream
@@ -281,10 +348,16 @@ def run_gpu(args) -> None:
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "replayed from profiles/traffic.json (one ncu --set full capture of this "
+                                  "kernel on this workload), not measured in this run",
+                "peak_source": peak_src,
                 "algorithmic_bytes": b_alg, "kernel": "k_fused_sell<double,add,plain>",
                 "kernel_ms_mean": kern_ms, "kernel_ms_min": per[0], "kernel_ms_median": per[len(per) // 2],
                 "frac_vs_8TBps": achieved / 8000.0}
+
+    check = run_check(X, g, world, n, ids_dev, ints_dev, hbuf, stream, dist)
+    del ids_dev, ints_dev
 
     if rank == 0:
         cb = None
@@ -309,11 +382,13 @@ def run_gpu(args) -> None:
                            "setup_s": t_setup, "method": "pairwise", "exchange": transport,
                            "halo_bytes_sent_per_rank_per_step": 8 * info["send_slots"]},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cb}
+                "roofline": roofline, "cpu_baseline": cb, "check": check}
         print(json.dumps(line), flush=True)
     X.gs_free(g)
     if dist is not None:
         dist.destroy_process_group()
+    if not check["ok"]:
+        raise SystemExit("bench.py: the correctness check of the timed handle failed: " + json.dumps(check))
 
 
 def main() -> None:

@@ -65,7 +65,9 @@ __device__ __forceinline__ T apply(T a, T b)
   if (OP == XO_MUL) return a * b;
   if (OP == XO_MIN) return (b < a) ? b : a;
   if (OP == XO_MAX) return (b > a) ? b : a;
-  // binary-prefix (src/gs_defs.h:37-42): longest common leading bit string
+  // binary-prefix (src/gs_defs.h:37-42): longest common leading bit string.
+  // Like the reference's macro it is instantiated for every domain through a
+  // conversion to unsigned (meaningful for non-negative values below 2^32).
   if (b != (T)0) {
     unsigned a_ = (unsigned)a, b_ = (unsigned)b;
     if (a_ == 0u) return (T)b_;
@@ -799,10 +801,7 @@ static inline unsigned bnd_blocks(size_t nb)
     case XO_MUL: X(T, XO_MUL, MODE); break;                                   \
     case XO_MIN: X(T, XO_MIN, MODE); break;                                   \
     case XO_MAX: X(T, XO_MAX, MODE); break;                                   \
-    case XO_BPR:                                                              \
-      if (xdom == XD_I32 || xdom == XD_I64) { X(T, XO_BPR, MODE); }           \
-      else exags_fail(1, __FILE__, __LINE__, "gs: gs_bpr is defined on integer domains only"); \
-      break;                                                                  \
+    case XO_BPR: X(T, XO_BPR, MODE); break;                                   \
     default: exags_fail(1, __FILE__, __LINE__, "gs: bad op %d", xop);         \
   }
 #define FOR_DOM(MODE, X)                                                      \

@@ -266,13 +266,17 @@ static void field_of(struct xcu_field *f, void *const *ptrs, int mode, unsigned 
 /* Decide whether this rank takes part in an exchange and get the buffers.
    The pull and push transports have collective steps (host barriers, mailbox
    growth): there a rank takes part whenever any rank has something to send. */
-static void bnd_prepare(struct gs_data *g, struct bnd_ctx *c, unsigned vn, int xd, int transpose)
+static void bnd_prepare(struct gs_data *g, struct bnd_ctx *c, unsigned vn, int xd, int xop, int transpose)
 {
   struct xg_world *w = g->w;
   const struct xg_plan *pl = &g->plan;
   const unsigned esz = xg_dom_bytes(xd);
   memset(c, 0, sizeof *c);
   c->allred = g->method == gs_all_reduce;
+  /* gs_bpr has no NCCL reduction (allreduce_exec goes through comm_allreduce,
+     which knows every op, src/gs.upc:1006-1026): such calls take the pairwise
+     plan, which every handle has and which gives the same values */
+  if (c->allred && xop == XO_BPR && !xg_world_ipc(w)) c->allred = 0;
   c->push = xg_world_push(w) && !c->allred;
   c->active = xg_world_np(w) > 1 &&
     (c->allred || ((c->push || xg_world_ipc(w)) ? pl->max_total > 0 : pl->nb > 0));
@@ -382,7 +386,7 @@ static void gs_enqueue_traced(struct gs_data *g, void *const *ptrs, int mode, un
   static void *ev[6];
   if (!ev[0]) for (int i = 0; i < 6; ++i) ev[i] = xcu_event_create_timed();
   struct bnd_ctx bc;
-  bnd_prepare(g, &bc, vn, xd, transpose);
+  bnd_prepare(g, &bc, vn, xd, xop, transpose);
   xcu_event_record(ev[0], stream);
   if (bc.active) bnd_pack_phase(g, &bc, ptrs, mode, vn, xd, xop, transpose, stream, 1);
   xcu_event_record(ev[1], stream);
@@ -436,7 +440,7 @@ static void gs_enqueue(struct gs_data *g, void *const *ptrs, int mode, unsigned 
   void *scomm = xg_world_stream(w, 1);
   if (g_trace < 0) { const char *v = getenv("EXAGS_TRACE"); g_trace = v ? atoi(v) : 0; }
   if (g_trace > 0) { gs_enqueue_traced(g, ptrs, mode, vn, xd, xop, transpose, stream, wgt); return; }
-  bnd_prepare(g, &bc, vn, xd, transpose);
+  bnd_prepare(g, &bc, vn, xd, xop, transpose);
   if (bc.active) {
     /* fork: boundary stream starts after whatever precedes us on `stream` */
     xcu_event_record(xg_world_event(w, 0), stream);
@@ -515,7 +519,7 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
      sit in the first and last layers of a slab); the chunks they touch go
      back after the unpack, every other chunk as soon as its windows are done */
   struct bnd_ctx bc;
-  bnd_prepare(g, &bc, vn, xd, transpose);
+  bnd_prepare(g, &bc, vn, xd, xop, transpose);
   u32 done = 0;
   for (unsigned k = 0; k < C; ++k) {
     size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;

@@ -587,3 +587,67 @@ void ogs_exec1(ogs *h, void *u, int mode, unsigned vn, int dom, int op, int tran
   void *uu[1] = { u };
   ogs_exec(h, uu, mode, vn, dom, op, transpose);
 }
+
+/* ---- the public gs_local.h entry points (src/gs_local.h:23-41) -------------
+   One dispatcher for the fourteen of them, restated on the strided kernels
+   above exactly as src/gs_local.c composes them:
+     gs_gather_array / gs_init_array    src/gs_local.c:187-201 (n in `vn`, no map)
+     gs_gather / gs_scatter / gs_init   :206-230  (vn ignored)
+     *_vec                              :114-158,235-251  (tuples of vn)
+     *_many                             :256-288  (vn arrays, plain kernel on each)
+     gs_gather_vec_to_many              :295-307  out = vn arrays, in = [slot][vn]
+     gs_scatter_many_to_vec             :309-319  out = [slot][vn], in = vn arrays
+     gs_scatter_vec_to_many             :321-331  out = vn arrays, in = [slot][vn]
+   tests/test_oracle_pin.py pins it to the reference's compiled gs_local.c.     */
+enum { L_GATHER_ARRAY, L_INIT_ARRAY, L_GATHER, L_SCATTER, L_INIT, L_GATHER_VEC, L_SCATTER_VEC, L_INIT_VEC,
+       L_GATHER_MANY, L_SCATTER_MANY, L_INIT_MANY, L_GATHER_VEC_TO_MANY, L_SCATTER_MANY_TO_VEC,
+       L_SCATTER_VEC_TO_MANY };
+void ogs_local(int which, void *out, const void *in, unsigned vn, const unsigned *map, int dom, int op)
+{
+  const unsigned sz = dom_size[dom];
+  void *const *po = (void *const *)out;
+  const void *const *pi = (const void *const *)in;
+  switch (which) {
+    case L_GATHER_ARRAY: {            /* dense: element i of out OP= element i of in */
+      uint *idm = (uint *)zalloc(((size_t)3 * vn + 1) * sizeof(uint));
+      for (uint i = 0; i < vn; ++i) { idm[3 * i] = i; idm[3 * i + 1] = i; idm[3 * i + 2] = NIL; }
+      idm[3 * (size_t)vn] = NIL;
+      gather_any(out, 1, in, 1, idm, dom, op);
+      free(idm);
+      break;
+    }
+    case L_INIT_ARRAY: {
+      uint *idm = (uint *)zalloc(((size_t)vn + 1) * sizeof(uint));
+      for (uint i = 0; i < vn; ++i) idm[i] = i;
+      idm[vn] = NIL;
+      init_any(out, 1, idm, dom, op);
+      free(idm);
+      break;
+    }
+    case L_GATHER:  gather_any(out, 1, in, 1, map, dom, op); break;
+    case L_SCATTER: scatter_any(out, 1, in, 1, map, dom); break;
+    case L_INIT:    init_any(out, 1, map, dom, op); break;
+    case L_GATHER_VEC:
+      for (unsigned k = 0; k < vn; ++k) gather_any((char *)out + k * sz, vn, (const char *)in + k * sz, vn, map, dom, op);
+      break;
+    case L_SCATTER_VEC:
+      for (unsigned k = 0; k < vn; ++k) scatter_any((char *)out + k * sz, vn, (const char *)in + k * sz, vn, map, dom);
+      break;
+    case L_INIT_VEC:
+      for (unsigned k = 0; k < vn; ++k) init_any((char *)out + k * sz, vn, map, dom, op);
+      break;
+    case L_GATHER_MANY:  for (unsigned k = 0; k < vn; ++k) gather_any(po[k], 1, pi[k], 1, map, dom, op); break;
+    case L_SCATTER_MANY: for (unsigned k = 0; k < vn; ++k) scatter_any(po[k], 1, pi[k], 1, map, dom); break;
+    case L_INIT_MANY:    for (unsigned k = 0; k < vn; ++k) init_any(po[k], 1, map, dom, op); break;
+    case L_GATHER_VEC_TO_MANY:
+      for (unsigned k = 0; k < vn; ++k) gather_any(po[k], 1, (const char *)in + k * sz, vn, map, dom, op);
+      break;
+    case L_SCATTER_MANY_TO_VEC:
+      for (unsigned k = 0; k < vn; ++k) scatter_any((char *)out + k * sz, vn, pi[k], 1, map, dom);
+      break;
+    case L_SCATTER_VEC_TO_MANY:
+      for (unsigned k = 0; k < vn; ++k) scatter_any(po[k], 1, (const char *)in + k * sz, vn, map, dom);
+      break;
+    default: fprintf(stderr, "oracle: ogs_local: bad entry %d\n", which); exit(1);
+  }
+}

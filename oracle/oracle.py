@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
         L.ogs_neighbours.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint]
         L.ogs_exec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int]
         L.ogs_unique.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ogs_local.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -109,3 +110,25 @@ def unique(ids_per_rank) -> None:
     tab = (C.c_void_p * len(ids_per_rank))(*[a.ctypes.data for a in ids_per_rank])
     ns = (C.c_uint * len(ids_per_rank))(*[a.size for a in ids_per_rank])
     lib().ogs_unique(len(ids_per_rank), tab, ns)
+
+
+# the public gs_local.h entry points (src/gs_local.h:23-41), in ogs_local's numbering
+LOCAL_ENTRIES = ["gs_gather_array", "gs_init_array", "gs_gather", "gs_scatter", "gs_init",
+                 "gs_gather_vec", "gs_scatter_vec", "gs_init_vec", "gs_gather_many", "gs_scatter_many",
+                 "gs_init_many", "gs_gather_vec_to_many", "gs_scatter_many_to_vec", "gs_scatter_vec_to_many"]
+
+
+def local(name: str, out, inp, vn: int, map_, dom: int, op: int) -> None:
+    """One gs_local.h entry point on host arrays, in place on `out`.  out / inp:
+    ndarray, or a list of vn ndarrays where the entry point takes an array of
+    pointers; vn is the element count for the two *_array entries."""
+    def ptr(x):
+        if x is None:
+            return None, None
+        if isinstance(x, (list, tuple)):
+            t = (C.c_void_p * len(x))(*[a.ctypes.data for a in x])
+            return C.addressof(t), t
+        return x.ctypes.data, None
+    po, k1 = ptr(out)
+    pi, k2 = ptr(inp)
+    lib().ogs_local(LOCAL_ENTRIES.index(name), po, pi, vn, map_.ctypes.data if map_ is not None else None, dom, op)

@@ -72,3 +72,33 @@ def run(ids_per_rank, cases, data, unique=0, method=1, want_maps=False, reps=0, 
                 o += L
             out_maps.append(row)
     return out_maps, times
+
+
+def local(name: str, out, inp, vn: int, map_, dom: int, op: int) -> None:
+    """The reference's own compiled gs_local.c entry point `name`
+    (src/gs_local.h:23-41; Nek flavour symbols gslib_*), same calling convention
+    as oracle.local.  Pure C, called in this process."""
+    L = C.CDLL(LIB)
+
+    def ptr(x):
+        if isinstance(x, (list, tuple)):
+            t = (C.c_void_p * len(x))(*[a.ctypes.data for a in x])
+            return C.c_void_p(C.addressof(t)), t
+        return C.c_void_p(x.ctypes.data), None
+    po, k1 = ptr(out)
+    f = getattr(L, "gslib_" + name)
+    f.restype = None
+    mp = C.c_void_p(map_.ctypes.data) if map_ is not None else None
+    if name == "gs_gather_array":
+        pi, k2 = ptr(inp)
+        f(po, pi, C.c_uint(vn), C.c_int(dom), C.c_int(op))
+    elif name == "gs_init_array":
+        f(po, C.c_uint(vn), C.c_int(dom), C.c_int(op))
+    elif "init" in name:
+        f(po, C.c_uint(vn), mp, C.c_int(dom), C.c_int(op))
+    elif "gather" in name:
+        pi, k2 = ptr(inp)
+        f(po, pi, C.c_uint(vn), mp, C.c_int(dom), C.c_int(op))
+    else:
+        pi, k2 = ptr(inp)
+        f(po, pi, C.c_uint(vn), mp, C.c_int(dom))

@@ -33,6 +33,8 @@ def gs_test_fixture_ids(np_, rank):
 def values(n, dtype, op, seed):
     rng = np.random.default_rng(seed)
     dtype = np.dtype(dtype)
+    if op == "bpr":           # common binary prefix of unsigned values (src/gs_defs.h:37-42)
+        return rng.integers(0, 1 << 20, size=n).astype(dtype)
     if dtype.kind == "f":
         return rng.uniform(0.5, 1.5, size=n).astype(dtype)
     if op == "mul":
@@ -42,3 +44,4 @@ def values(n, dtype, op, seed):
 
 DTYPES = {"double": np.float64, "float": np.float32, "int": np.int32, "long": np.int64}
 OPS = ["add", "mul", "min", "max"]
+OPS_BPR = OPS + ["bpr"]     # gs_op order (src/gs_defs.h:73-79); bpr is what xxt.upc:623 issues

@@ -129,9 +129,11 @@ def main():
                         print(f"MISMATCH case={case} rank={r} map={w} (device-built handle)")
                         ok = False
         combos = list(itertools.product(cases.DTYPES.items(), cases.OPS, (0, 1), (0, 1, 2)))
+        # gs_bpr (xxt.upc:623 calls it on sint): every method, incl. all_reduce / auto over NCCL
+        combos += [(("int", np.int32), "bpr", 0, 0), (("long", np.int64), "bpr", 1, 1), (("double", np.float64), "bpr", 0, 2)]
         for (dname, dt), op, t, mode in combos:
             vn = 1 if mode == 0 else 3
-            opi = cases.OPS.index(op)
+            opi = cases.OPS_BPR.index(op)
             dom = X.NP_DOM[np.dtype(dt)]
             if mode == 2:
                 u = [cases.values(ids.size, dt, op, 1000 * rank + k) for k in range(vn)]

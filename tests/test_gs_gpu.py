@@ -93,15 +93,29 @@ def test_host_pointers_staged(X, O):
     X.gs_free(g)
 
 
-def test_bpr_integer(X, O):
-    ids = cases.random_ids(2000, 300, 9, p_flag=0.0)
+@pytest.mark.parametrize("dname", list(cases.DTYPES))
+def test_bpr_every_domain(X, O, dname):
+    """gs_bpr (binary prefix, src/gs_defs.h:37-42; xxt.upc:623 issues it on sint):
+    the reference instantiates it for every domain through a conversion to uint."""
+    dt = cases.DTYPES[dname]
+    ids = cases.random_ids(2000, 300, 9, p_flag=0.2)
     g, o = X.gs_setup(ids), O.Oracle([ids])
-    u = np.random.default_rng(1).integers(0, 1 << 20, size=ids.size).astype(np.int32)
-    want = u.copy()
-    o.exec([want], O.M_PLAIN, 1, O.D_INT, O.O_BPR, 0)
-    d = _dev(u)
-    X.gs(d, X.gs_int, X.gs_bpr, 0, g)
-    assert np.array_equal(d.cpu().numpy(), want)
+    for t, (mode, vn) in itertools.product((0, 1), ((0, 1), (1, 3), (2, 2))):
+        if mode == 2:
+            u = [cases.values(ids.size, dt, "bpr", 3 + k) for k in range(vn)]
+            want = [x.copy() for x in u]
+            o.exec([want], mode, vn, O.NP_DOM[np.dtype(dt)], O.O_BPR, t)
+            d = [_dev(x) for x in u]
+            X.gs_many(d, vn, X.NP_DOM[np.dtype(dt)], X.gs_bpr, t, g)
+            assert all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(d, want))
+            continue
+        u = cases.values(ids.size * vn, dt, "bpr", 3)
+        want = u.copy()
+        o.exec([want], mode, vn, O.NP_DOM[np.dtype(dt)], O.O_BPR, t)
+        d = _dev(u)
+        (X.gs(d, X.NP_DOM[np.dtype(dt)], X.gs_bpr, t, g) if mode == 0
+         else X.gs_vec(d, vn, X.NP_DOM[np.dtype(dt)], X.gs_bpr, t, g))
+        assert np.array_equal(d.cpu().numpy(), want), f"{dname} t={t} mode={mode}"
     X.gs_free(g)
 
 
@@ -210,6 +224,46 @@ def test_full_size_properties(X):
     want = torch.zeros(c["unique"] + 1, dtype=torch.int64, device="cuda").scatter_add_(0, idt, iv)[idt]
     X.gs(iv, X.gs_long, X.gs_add, 0, g)
     assert torch.equal(iv, want)                       # integer add is exact
+    X.gs_free(g)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32, torch.int32])
+def test_config3_full_size(X, dt):
+    """BASELINE config 3 at full size (M7, 3 components): gs_vec and gs_many
+    give, component by component, exactly what three plain gs calls give (same
+    association order) -- a size-independent property for sizes the CPU oracle
+    cannot reach (src/gs_local.c:114-158,256-288 against :60-97)."""
+    dom = {torch.float64: X.gs_double, torch.float32: X.gs_float, torch.int32: X.gs_int}[dt]
+    ids = semmesh.box_ids(64, 64, 48, 7)
+    n = ids.size
+    g = X.gs_setup(ids)
+    del ids
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    if dt.is_floating_point:
+        comps = [torch.rand(n, dtype=dt, device="cuda", generator=gen) + 0.5 for _ in range(3)]
+    else:
+        comps = [torch.randint(-1000, 1001, (n,), dtype=dt, device="cuda", generator=gen) for _ in range(3)]
+    for op in (X.gs_add, X.gs_max):
+        want = [c.clone() for c in comps]
+        for c in want:
+            X.gs(c, dom, op, 0, g)
+        many = [c.clone() for c in comps]
+        X.gs_many(many, 3, dom, op, 0, g)
+        assert all(torch.equal(a, b) for a, b in zip(many, want)), "gs_many != 3 x gs"
+        del many
+        vec = torch.stack(comps, dim=1).contiguous().view(-1)
+        X.gs_vec(vec, 3, dom, op, 0, g)
+        assert torch.equal(vec.view(n, 3), torch.stack(want, dim=1)), "gs_vec != 3 x gs"
+        del vec
+        if dt.is_floating_point and op == X.gs_add:
+            w = torch.rand(n, dtype=dt, device="cuda", generator=gen) * 0.75 + 0.25
+            m = torch.ones(n, dtype=dt, device="cuda")
+            X.gs(m, dom, X.gs_add, 0, g)
+            fused = comps[0].clone()
+            X.gs_weighted(fused, w, dom, X.gs_add, g)
+            assert torch.equal(fused, torch.where(m > 1, want[0] * w, want[0])), "gs_weighted != gs then *w"
+            del w, m, fused
+        del want
     X.gs_free(g)
 
 

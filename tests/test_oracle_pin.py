@@ -4,6 +4,7 @@ running the reference's code), the assertions of the reference's own
 tests/gs/gs_test.upc:118-240, and the golden fixtures under tests/golden/
 generated from the compiled reference sources by oracle/make_golden.py."""
 import glob
+import itertools
 import os
 
 import numpy as np
@@ -13,6 +14,11 @@ import cases
 from exags_b200 import semmesh
 
 NIL = 0xFFFFFFFF
+
+
+def _ref_ok():
+    import ref
+    return ref.available()
 
 
 def sent(*xs):
@@ -120,3 +126,28 @@ def test_golden_from_reference(O, path):
             else:
                 assert np.array_equal(got, want), (path, k, r)
         k += 1
+
+
+@pytest.mark.skipif(not _ref_ok(), reason="oracle/_ref (the reference's compiled sources) not built")
+@pytest.mark.parametrize("name", list(__import__("local_cases").ENTRIES))
+def test_local_entry_points_against_reference(O, name):
+    """ogs_local (the oracle's restatement of the 14 public gs_local.h entry
+    points, src/gs_local.h:23-41) against the reference's own compiled
+    gs_local.c, every domain and op, bit for bit."""
+    import copy
+    import local_cases as LC
+    import ref
+    table = LC.maps(O)
+    for (dname, dt), op in itertools.product(cases.DTYPES.items(), cases.OPS_BPR):
+        if not LC.ENTRIES[name][4] and op != "add":
+            continue
+        out, inp, vn, mp = LC.make(name, table, dt, op)
+        a_out = copy.deepcopy(out)
+        a_in = a_out if inp is out else copy.deepcopy(inp)
+        b_out = copy.deepcopy(out)
+        b_in = b_out if inp is out else copy.deepcopy(inp)
+        dom, opi = O.NP_DOM[np.dtype(dt)], cases.OPS_BPR.index(op)
+        O.local(name, a_out, a_in, vn, mp, dom, opi)
+        ref.local(name, b_out, b_in, vn, mp, dom, opi)
+        same = all(np.array_equal(x, y) for x, y in zip(a_out, b_out)) if isinstance(out, list) else np.array_equal(a_out, b_out)
+        assert same, f"{name} {dname} {op}"

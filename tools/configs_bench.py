@@ -1,7 +1,19 @@
 """Device-resident timing of the BASELINE.json configurations beyond the headline one
-(config 3: gs_vec / gs_many with 3 components in float and double; other domains/ops;
-the CSR path used for flagged labels).  Prints one line per case with algorithmic bytes
-and fraction of the measured HBM peak.   python tools/configs_bench.py [--ez 48]"""
+(config 3: gs_vec / gs_many with 3 components in float and double; other domains/ops; maps with
+flagged labels; unique=1 handles as amg.upc builds them; the weighted gs; comm_dot) on M7.
+One line per case: ms, GDOF/s, algorithmic bytes and fraction of the measured HBM peak.
+
+    python tools/configs_bench.py [--ez 48] [--steps 20] [--only SUBSTR] [--ncu]
+
+--ncu: every case is warmed up as usual and then run ONCE between cudaProfilerStart/Stop, so
+    ncu --profile-from-start off --set full ... python tools/configs_bench.py --ncu
+captures exactly one launch of every kernel on the list (no timing is printed in that mode).
+
+Algorithmic bytes: 32 B for every distinct sector of the field(s)
+holding a member that is read, 32 B for every distinct sector holding a member that is written,
+4 B per member index and per group offset, plus what the variant adds (one weight per member;
+one identity store per flagged single).  For maps with flagged labels the read and written member
+sets differ (src/gs.upc:1181-1184), so both are counted from the handle's own maps."""
 import argparse
 import json
 import os
@@ -9,6 +21,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "exaflow-exags-upc_b200")]
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import exags_b200 as X  # noqa: E402
 from exags_b200 import semmesh  # noqa: E402
@@ -17,6 +30,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ez", type=int, default=48)
 ap.add_argument("--order", type=int, default=7)
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--only", default="")
+ap.add_argument("--ncu", action="store_true")
 args = ap.parse_args()
 peak = 6556.5
 try:
@@ -26,29 +41,64 @@ except Exception:
 dims = (64, 64, args.ez, args.order)
 ids = semmesh.box_ids(*dims)
 n = ids.size
-g = X.gs_setup(ids)
-info = g.info()
-G, S = info["groups"], info["members"]
 stream = torch.cuda.current_stream().cuda_stream
 DT = {X.gs_double: torch.float64, X.gs_float: torch.float32, X.gs_int: torch.int32, X.gs_long: torch.int64}
+NIL = 0xFFFFFFFF
 
 
-def sectors(esz, vn):
-    # distinct 32 B sectors touched: every sector at N=7 for 4- and 8-byte types (computed for f64 by the library)
-    return info["sectors_f64"] * esz * vn / 8.0 if esz * vn >= 8 else info["sectors_f64"] / 2.0
+def sector_counts(handle, esz, vn_tuple, transpose):
+    """(sectors read, sectors written, members, groups, flagged singles) of one call on a T[n][vn_tuple]
+    field, from the handle's own sentinel maps: map 1 = every group in full, map 0 = unflagged members only.
+    transpose 0 reads map 0's members and writes map 1's; transpose 1 the other way round."""
+    def members_of(which):
+        m = torch.from_numpy(handle.dump_map(which).astype(np.int64)).cuda()
+        return m[m != NIL], int((m == NIL).sum().item()) - 1
+
+    def nsec(idx):
+        if idx.numel() == 0:
+            return 0
+        lo = (idx * (esz * vn_tuple)) // 32
+        hi = (idx * (esz * vn_tuple) + esz * vn_tuple - 1) // 32
+        mark = torch.zeros(int(hi.max().item()) + 1, dtype=torch.bool, device="cuda")
+        for k in range(int((hi - lo).max().item()) + 1):
+            mark[torch.minimum(lo + k, hi)] = True
+        return int(mark.sum().item())
+    full, G = members_of(1)
+    info = handle.info()
+    unf, _ = members_of(0)
+    if unf.numel() == full.numel() and info["flagged_primaries"] == 0:
+        s = nsec(full)
+        return s, s, full.numel(), G, 0
+    fp = torch.from_numpy(handle.dump_map(2).astype(np.int64)).cuda()
+    fp = fp[fp != NIL]
+    rd, wr = (unf, torch.cat([full, fp])) if not transpose else (full, unf)
+    return nsec(rd), nsec(wr), full.numel(), G, info["flagged_singles"]
 
 
-def run(name, mode, vn, dom, op, handle=g, idx_bytes=None):
+def run(name, mode, vn, dom, op, handle, transpose=0, weighted=False, secs=None):
+    if args.only and args.only not in name:
+        return
     dt = DT[dom]
     esz = torch.empty(0, dtype=dt).element_size()
     if mode == X.mode_many:
         u = [torch.ones(n, dtype=dt, device="cuda") for _ in range(vn)]
     else:
         u = torch.ones(n * vn, dtype=dt, device="cuda")
-    call = lambda: X.gs_async(u, mode, vn, dom, op, 0, handle, stream)
+    w = torch.full((n,), 0.5, dtype=dt, device="cuda") if weighted else None
+    if weighted:
+        call = lambda: X.gs_weighted(u, w, dom, op, handle, stream)
+    else:
+        call = lambda: X.gs_async(u, mode, vn, dom, op, transpose, handle, stream)
     for _ in range(3):
         call()
     torch.cuda.synchronize()
+    if args.ncu:
+        torch.cuda.profiler.start()
+        call()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(f"{name}: captured", flush=True)
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -56,40 +106,64 @@ def run(name, mode, vn, dom, op, handle=g, idx_bytes=None):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    b_alg = 2 * 32 * sectors(esz, vn) + (4 * S + 4 * (G + 1) if idx_bytes is None else idx_bytes)
-    print(f"{name:34s} {ms:8.4f} ms  {n / ms / 1e6:8.1f} GDOF/s  B_alg {b_alg / n:6.2f} B/DOF  "
+    tuple_ = vn if mode == X.mode_vec else 1
+    comps = vn if mode == X.mode_many else 1
+    key = (id(handle), esz, tuple_, transpose)
+    if key not in SEC:
+        SEC[key] = sector_counts(handle, esz, tuple_, transpose)
+    rd, wr, S, G, nfs = SEC[key]
+    b_alg = 32 * (rd + wr) * comps + 4 * S + 4 * (G + 1) + (esz * S if weighted else 0) + 4 * nfs
+    print(f"{name:46s} {ms:8.4f} ms  {n / ms / 1e6:8.1f} GDOF/s  B_alg {b_alg / n:6.2f} B/DOF  "
           f"{b_alg / ms / 1e6:7.0f} GB/s  frac {b_alg / ms / 1e6 / peak:.3f}", flush=True)
 
 
-print(f"mesh 64x64x{args.ez} N={args.order}: n={n} G={G} S={S}")
-run("gs(add,double)", X.mode_plain, 1, X.gs_double, X.gs_add)
-run("gs(add,float)", X.mode_plain, 1, X.gs_float, X.gs_add)
-run("gs(max,int)", X.mode_plain, 1, X.gs_int, X.gs_max)
-run("gs(min,long)", X.mode_plain, 1, X.gs_long, X.gs_min)
-run("gs(mul,double)", X.mode_plain, 1, X.gs_double, X.gs_mul)
-run("gs_vec(3,add,double)", X.mode_vec, 3, X.gs_double, X.gs_add)
-run("gs_vec(3,add,float)", X.mode_vec, 3, X.gs_float, X.gs_add)
-run("gs_many(3,add,double)", X.mode_many, 3, X.gs_double, X.gs_add)
-run("gs_many(3,add,float)", X.mode_many, 3, X.gs_float, X.gs_add)
+SEC = {}
+g = X.gs_setup(ids)
+info = g.info()
+print(f"mesh 64x64x{args.ez} N={args.order}: n={n} G={info['groups']} S={info['members']}")
+run("gs(add,double)", X.mode_plain, 1, X.gs_double, X.gs_add, g)
+run("gs(add,float)", X.mode_plain, 1, X.gs_float, X.gs_add, g)
+run("gs(max,int)", X.mode_plain, 1, X.gs_int, X.gs_max, g)
+run("gs(min,long)", X.mode_plain, 1, X.gs_long, X.gs_min, g)
+run("gs(mul,double)", X.mode_plain, 1, X.gs_double, X.gs_mul, g)
+run("gs_vec(3,add,double)", X.mode_vec, 3, X.gs_double, X.gs_add, g)
+run("gs_vec(3,add,float)", X.mode_vec, 3, X.gs_float, X.gs_add, g)
+run("gs_many(3,add,double)", X.mode_many, 3, X.gs_double, X.gs_add, g)
+run("gs_many(3,add,float)", X.mode_many, 3, X.gs_float, X.gs_add, g)
+run("gs_weighted(add,double)", X.mode_plain, 1, X.gs_double, X.gs_add, g, weighted=True)
+run("gs_weighted(add,float)", X.mode_plain, 1, X.gs_float, X.gs_add, g, weighted=True)
 # comm_dot on two device vectors of n doubles: 16 B per element, HBM-bound
-va, vb = torch.ones(n, dtype=torch.float64, device="cuda"), torch.full((n,), 0.5, dtype=torch.float64, device="cuda")
-for _ in range(3):
-    X.comm_dot(va, vb)
-import time as _t
-torch.cuda.synchronize(); t0 = _t.perf_counter()
-for _ in range(args.steps):
-    r = X.comm_dot(va, vb)
-ms = 1e3 * (_t.perf_counter() - t0) / args.steps
-assert r == 0.5 * n
-print(f"{'comm_dot(device, n doubles)':34s} {ms:8.4f} ms  (blocking call incl. the scalar D2H)  "
-      f"{16 * n / ms / 1e6:7.0f} GB/s  frac {16 * n / ms / 1e6 / peak:.3f}", flush=True)
-del va, vb
+if not args.only or "comm_dot" in args.only:
+    va, vb = torch.ones(n, dtype=torch.float64, device="cuda"), torch.full((n,), 0.5, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        X.comm_dot(va, vb)
+    if args.ncu:
+        torch.cuda.profiler.start(); X.comm_dot(va, vb); torch.cuda.profiler.stop()
+    else:
+        import time as _t
+        torch.cuda.synchronize(); t0 = _t.perf_counter()
+        for _ in range(args.steps):
+            r = X.comm_dot(va, vb)
+        ms = 1e3 * (_t.perf_counter() - t0) / args.steps
+        assert r == 0.5 * n
+        print(f"{'comm_dot(device, n doubles), blocking':46s} {ms:8.4f} ms  (incl. the scalar D2H)  "
+              f"{16 * n / ms / 1e6:7.0f} GB/s  frac {16 * n / ms / 1e6 / peak:.3f}", flush=True)
+    del va, vb
 X.gs_free(g)
-# flagged labels -> CSR path with per-group unflagged counts
-ids2 = ids.copy()
-ids2[::7] = -ids2[::7]
-g2 = X.gs_setup(ids2)
-i2 = g2.info()
-G, S = i2["groups"], i2["members"]
-run("gs(add,double) flagged 1-in-7 (sliced + init list)", X.mode_plain, 1, X.gs_double, X.gs_add, g2, idx_bytes=4 * S + 8 * G + 4)
-X.gs_free(g2)
+# the flagged case real callers produce: a unique=1 handle (src/amg.upc: gs_setup(..., 1, gs_auto, 1)).
+# Every label keeps one unflagged copy: transpose 0 copies it to the others, transpose 1 sums into it.
+if not args.only or "unique" in args.only:
+    gu = X.gs_setup(ids, unique=1)
+    run("unique=1 handle: gs(add,double) t=0", X.mode_plain, 1, X.gs_double, X.gs_add, gu, transpose=0)
+    run("unique=1 handle: gs(add,double) t=1", X.mode_plain, 1, X.gs_double, X.gs_add, gu, transpose=1)
+    run("unique=1 handle: gs(add,float) t=1", X.mode_plain, 1, X.gs_float, X.gs_add, gu, transpose=1)
+    X.gs_free(gu)
+# a synthetic pattern with flagged singles and partly flagged groups
+if not args.only or "1-in-7" in args.only:
+    ids2 = ids.copy()
+    ids2[::7] = -ids2[::7]
+    g2 = X.gs_setup(ids2)
+    del ids2
+    run("flagged 1-in-7: gs(add,double) t=0", X.mode_plain, 1, X.gs_double, X.gs_add, g2, transpose=0)
+    run("flagged 1-in-7: gs(add,double) t=1", X.mode_plain, 1, X.gs_double, X.gs_add, g2, transpose=1)
+    X.gs_free(g2)

@@ -1,0 +1,68 @@
+"""A/B timing on M7 of the layout knobs that are read at gs_setup time, one handle per setting,
+interleaved so that drift hits every setting alike:  python tools/knob_bench.py
+    EXAGS_SELL_LINE_SHIFT=5   chain ordering on 32-element lines (the line of a 4-byte field)
+    EXAGS_SELL_COMPRESS=1     16-bit index stream (k_fused_sell_c)
+for gs(add) on double, float, and gs_vec(3, float)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "exaflow-exags-upc_b200")]
+import torch  # noqa: E402
+import exags_b200 as X  # noqa: E402
+from exags_b200 import semmesh  # noqa: E402
+
+peak = 6556.5
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+ids = semmesh.box_ids(64, 64, 48, 7)
+n = ids.size
+KNOBS = ("EXAGS_SELL_LINE_SHIFT", "EXAGS_SELL_COMPRESS")
+
+
+def handle(**env):
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update({k: str(v) for k, v in env.items()})
+    g = X.gs_setup(ids)
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    return g
+
+
+H = {"default": handle(), "line_shift=5": handle(EXAGS_SELL_LINE_SHIFT=5), "compress": handle(EXAGS_SELL_COMPRESS=1),
+     "compress+line_shift=5": handle(EXAGS_SELL_COMPRESS=1, EXAGS_SELL_LINE_SHIFT=5)}
+info = H["default"].info()
+G, S, nsec = info["groups"], info["members"], info["sectors_f64"]
+stream = torch.cuda.current_stream().cuda_stream
+for label, mode, vn, dom, dt in (("gs(add,double)", X.mode_plain, 1, X.gs_double, torch.float64),
+                                 ("gs(add,float)", X.mode_plain, 1, X.gs_float, torch.float32),
+                                 ("gs(max,int)", X.mode_plain, 1, X.gs_int, torch.int32),
+                                 ("gs_vec(3,add,float)", X.mode_vec, 3, X.gs_float, torch.float32),
+                                 ("gs_vec(3,add,double)", X.mode_vec, 3, X.gs_double, torch.float64)):
+    esz = torch.empty(0, dtype=dt).element_size()
+    b_alg = 2 * 32 * (nsec * esz * vn / 8.0 if esz * vn >= 8 else nsec / 2.0) + 4 * S + 4 * (G + 1)
+    u = torch.ones(n * vn, dtype=dt, device="cuda")
+    best = {}
+    for rep in range(3):
+        for name, g in H.items():
+            if "compress" in name and vn != 1:
+                continue
+            for _ in range(3):
+                X.gs_async(u, mode, vn, dom, X.gs_add if dt.is_floating_point else X.gs_max, 0, g, stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                X.gs_async(u, mode, vn, dom, X.gs_add if dt.is_floating_point else X.gs_max, 0, g, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            best.setdefault(name, []).append(e0.elapsed_time(e1) / 20)
+            u.fill_(1)
+    for name, ts in best.items():
+        ms = sorted(ts)[len(ts) // 2]
+        print(f"{label:22s} {name:24s} {ms:.4f} ms (median of {len(ts)}: {' '.join(f'{t:.4f}' for t in ts)})  "
+              f"frac {b_alg / ms / 1e6 / peak:.3f}", flush=True)
