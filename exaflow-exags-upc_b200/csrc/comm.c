@@ -62,6 +62,7 @@ struct xg_world {
   void *stream[4];
   void *event[4];
   void *scratch[4];
+  void *dot_scratch;                 /* partial sums of comm_dot_async */
   size_t scratch_bytes[4];
   /* nccl */
   void *nccl_lib;
@@ -800,6 +801,26 @@ double exags_comm_dot(const comm_ptr cp, double *v, double *w, exags_uint n)
     for (exags_uint i = 0; i < n; ++i) s += v[i] * w[i];
   exags_comm_allreduce(cp, gs_double, gs_add, &s, 1, &b);
   return s;
+}
+
+/* Stream-ordered comm_dot (extension, include/exags_cuda.h): v, w and the
+   result are device memory, nothing returns to the host, the work is ordered on
+   `stream` -- so a CG iteration can chain gs_async, the dot and the vector
+   updates that consume it without a host round trip (and capture them in a
+   CUDA graph when np == 1).  Across ranks the partial sums are combined by
+   ncclAllReduce on the same stream.                                         */
+void exags_comm_dot_async(const comm_ptr cp, const double *v, const double *w, exags_uint n,
+                          double *d_out, void *stream)
+{
+  struct xg_world *wd = cp ? (struct xg_world *)cp->priv : 0;
+  if (!wd || !wd->has_cuda) xfail("comm_dot_async: no CUDA device");
+  if (((uintptr_t)v | (uintptr_t)w) & 15u) xfail("comm_dot_async: device vectors must be 16-byte aligned");
+  if (!wd->dot_scratch) wd->dot_scratch = xcu_malloc(((size_t)xcu_dot_parts() + 1) * sizeof(double));
+  xcu_dot(stream, v, w, n, (double *)wd->dot_scratch, d_out);
+  if (wd->np > 1) {
+    if (wd->use_ipc) xfail("comm_dot_async: ranks sharing one GPU have no stream-ordered all-reduce; use comm_dot");
+    xg_nccl_allreduce(wd, d_out, 1, XD_F64, XO_ADD, stream);
+  }
 }
 
 /* T comm_reduce__T(cp, op, in, n): fold a local host array, then across ranks

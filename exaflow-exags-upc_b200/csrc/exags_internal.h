@@ -154,7 +154,9 @@ void *xg_ipc_peer(struct xg_world *w, int rank);   /* mapped pointer to rank's b
    B200 counterpart of pw_exec_sends/pw_exec_recvs (src/gs.upc:409-468),
    whose upc_memput + polled flag it restates with peer stores.  A mailbox
    belongs to one gs handle; two data areas alternate by call parity.       */
-#define XG_MBOX_HDR 4096u            /* flags u32[np] at 0, CTA counter at 512 */
+#define XG_MBOX_HDR 4096u            /* flags u32[np] at 0, CTA counter at 512, exchange number at 520 */
+#define XG_MBOX_COUNTER 512u
+#define XG_MBOX_EPOCH 520u
 struct xg_mbox {
   void  *mine;                       /* header + 2 data areas                  */
   size_t data_bytes;                 /* bytes of one data area                 */
@@ -238,18 +240,6 @@ struct xcu_sell {
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose);
-/* device SELL map with the compressed index stream (sell_window.h: 16-bit
-   codes, per-window base + dictionary); experiment, EXAGS_SELL_COMPRESS=1    */
-struct xcu_csell {
-  u32 nblock;
-  const unsigned char *mask;      /* the start / phase masks of the raw map  */
-  const unsigned short *code;     /* [nblock*256]                             */
-  const u32 *hdr;                 /* [nwin*2] base, dictionary entries        */
-  const u32 *dict;                /* [nwin*256]                               */
-};
-/* plain fields (one component), maps without flagged members */
-void xcu_fused_sell_c(void *stream, const struct xcu_csell *m, const struct xcu_field *f,
-                      int xdom, int xop);
 void xcu_gather_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                      int mode, int xdom, int xop);
 
@@ -265,12 +255,20 @@ struct xcu_bnd {
 /* push transport: where the pack kernel stores (device tables of one handle,
    one direction, one parity) and whom it signals                            */
 struct xcu_push {
-  const unsigned long long *base;  /* [neighbours] peer data area, as an address   */
+  const unsigned long long *base;  /* [2 parities][par_stride] peer data area of each neighbour, as an address */
+  u32  par_stride;                 /* entries between the two parities of `base`    */
   const u32 *delta;                /* [neighbours] peer slot - my slot (mod 2^32)   */
   const unsigned char *snb;        /* [slot entries] neighbour number of each entry */
   const unsigned long long *sig;   /* [nsig] address of my flag in each neighbour   */
-  u32  nsig;                       /* 0: do not signal from this launch             */
-  u32  epoch;
+  u32  nsig;                       /* 0: do not signal (nor advance the epoch) from this launch */
+  /* The exchange number lives in device memory (a word of my own mailbox
+     header) so that a call can be captured in a CUDA graph and replayed: this
+     exchange is number *depoch + 1; the launch that signals stores it back.
+     epoch_imm != 0 (the transport timing of gs_setup, which copies with the
+     copy engine and so needs the parity on the host) names the number instead
+     and the signal kernel stores it into *depoch.                            */
+  u32 *depoch;
+  u32  epoch_imm;
   u32 *counter;                    /* CTA completion counter in my mailbox          */
   const u32 *start;                /* [nnb+1] first send slot of each neighbour (slot-ordered pack) */
   u32  nnb;
@@ -285,7 +283,9 @@ void xcu_bnd_pack_push(void *stream, const struct xcu_bnd *b, const struct xcu_f
                        int mode, int xdom, int xop, int transpose, unsigned bufvn,
                        const struct xcu_push *pp);
 void xcu_push_signal(void *stream, const struct xcu_push *pp);
-void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, u32 epoch,
+/* wait until the flags of `ranks` in my mailbox reach the current exchange
+   number (*depoch, or epoch_imm when non-zero)                               */
+void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, const u32 *depoch, u32 epoch_imm,
                    double timeout_s, int *status);
 
 /* fused local gather(+init)+scatter over every group of m                  */
@@ -299,9 +299,11 @@ void xcu_bnd_pack(void *stream, const struct xcu_bnd *b, const struct xcu_field 
                   int mode, int xdom, int xop, int transpose, void *sendbuf,
                   unsigned bufvn, int allreduce);
 /* boundary: fold recvbuf slots into u[primary], then scatter to members    */
+/* depoch != NULL (push transport): recvbuf is the data area of parity 0 and
+   the kernel adds (*depoch & 1) * par_bytes, the area of the current exchange */
 void xcu_bnd_unpack(void *stream, const struct xcu_bnd *b, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose, const void *recvbuf,
-                    unsigned bufvn, int allreduce);
+                    unsigned bufvn, int allreduce, const u32 *depoch, size_t par_bytes);
 unsigned xcu_dot_parts(void);
 void xcu_dot(void *stream, const double *v, const double *w, size_t n, double *scratch, double *out);
 void xcu_fill_identity(void *stream, void *out, size_t n, int xdom, int xop);
@@ -344,8 +346,8 @@ void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht);
 /* hall: every group with >= 2 members; fp: all flagged primaries; fs: flagged
    primaries that head no multi-member group; sectors: distinct 32-byte sectors
    of a double field that hold a member of hall                               */
-void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
-                     u32 **fs, u32 *nfs, u64 *sectors);
+void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, struct xcu_dmap *in, u32 **fp, u32 *nfp,
+                     u32 **fs, u32 *nfs, u64 *sectors);   /* in: hall + fs as one-member groups, or off == NULL: same as hall */
 /* several ranks: bgrp = the nb boundary groups named by the exchange plan
    (host array, ascending).  in = interior groups with >= 2 members, bnd = every
    boundary group (all members, unflagged counts), bnd2 = boundary groups with

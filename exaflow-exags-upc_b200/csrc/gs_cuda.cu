@@ -255,11 +255,11 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
   static_assert(!WGT || (KU == 1 && MODE == XM_PLAIN && !GONLY), "weights: plain fields, full gather-scatter");
   const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   const unsigned start = startph & 0x55u, ph = startph & 0xAAu;
-  unsigned in = 0u, out = 0u;                 // slots that contribute / are written
+  unsigned mem = 0u;                          // slots that hold a member
 #pragma unroll
-  for (int j = 0; j < 8; ++j) if (id0[j] != XG_NONE) in |= 1u << j;
-  out = in;
-  if (FLG) { if (transpose) out = in & (~flg | start); else in &= ~flg; }
+  for (int j = 0; j < 8; ++j) if (id0[j] != XG_NONE) mem |= 1u << j;
+  unsigned in = mem, out = mem;               // slots that contribute / are written
+  if (FLG) { if (transpose) out = mem & (~flg | start); else in = mem & ~flg; }
   if (GONLY) out &= start;
   // everything below addresses memory in "fetch order": id[], lin, lout
   u32 id[8];
@@ -273,6 +273,12 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
   // slots contribute and both are written, so the masks need no swapping
   const unsigned lin = FLG ? swap_pair_bits(in, ph) : in;
   const unsigned lout = (FLG || GONLY) ? swap_pair_bits(out, ph) : out;
+  // Every member is loaded, also one whose value does not contribute (a flagged
+  // member with transpose == 0): it is written afterwards, and an 8-byte store
+  // into a 32-byte sector that is not in L2 makes the memory system read the
+  // sector anyway -- as a load ahead of the store that read is overlapped like
+  // every other one (unique=1 handle, t=0, M7: 0.375 -> see profiles/r2_configs).
+  const unsigned lld = FLG ? swap_pair_bits(mem, ph) : mem;
   const size_t es = f.stride();
   for (unsigned k0 = 0; k0 < (ONE ? 1u : f.vn); k0 += KU) {
     T x[KU][8];
@@ -284,16 +290,20 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (FLG) x[kk][j] = ident<T, OP>();
-          if ((lin >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
+          if ((lld >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
+          if (FLG) x[kk][j] = ((lin >> j) & 1u) ? x[kk][j] : ident<T, OP>();
         }
       }
     T wv[WGT ? 8 : 1];
     if (WGT) {
+      // a one-member group (a flagged single: start bit, next slot empty) is no
+      // group result -- gs_init's identity goes there unweighted.  Such a lane
+      // slot has no phase, so slot order and fetch order agree for it.
+      const unsigned lw = FLG ? lout & ~(start & ~(mem >> 1)) : lout;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         wv[WGT ? j : 0] = (T)1;
-        if ((lout >> j) & 1u) wv[WGT ? j : 0] = __ldg(wgt + id[j]);
+        if ((lw >> j) & 1u) wv[WGT ? j : 0] = __ldg(wgt + id[j]);
       }
     }
 #pragma unroll
@@ -374,44 +384,8 @@ k_fused_w(xcu_csr m, T *__restrict__ u, const T *__restrict__ wgt, int transpose
   const u32 *idx = m.idx + b;
   T v = nred ? u[__ldg(idx)] : ident<T, OP>();
   for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, u[__ldg(idx + j)]);
+  if (nall == 1u) { u[__ldg(idx)] = v; return; }       // a flagged single: the identity, unweighted
   for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
-}
-
-// Compressed index stream (experiment, EXAGS_SELL_COMPRESS=1; format in
-// sell_window.h): the lane's 8 member indices arrive as 8 16-bit codes (one
-// 128-bit load instead of two) and are rebuilt from the window's base and its
-// small dictionary of member-to-primary distances, held in shared memory; the
-// rest is sell_lane as in k_fused_sell.  One CTA is one window.
-template <typename T, int OP, int MINB>
-__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
-k_fused_sell_c(xcu_csell m, Fld<T, XM_PLAIN> f)
-{
-  static_assert(XG_SELL_CW == XG_SELL_WB, "compressed windows: one CTA per window");
-  __shared__ u32 dict[256];
-  const u32 w = blockIdx.x;
-  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
-  const unsigned lane = threadIdx.x & 31u;
-  // every load below is independent of the others: one trip to memory, not three.
-  // The first 64 dictionary entries (two lines; a structured mesh uses 7) are
-  // fetched without waiting for the entry count, the rare rest after it.
-  const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.code + ((size_t)c * 32u + lane) * 8u));
-  const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
-  const uint2 hd = __ldg(reinterpret_cast<const uint2 *>(m.hdr) + w);
-  if (threadIdx.x < 64u) dict[threadIdx.x] = __ldg(m.dict + (size_t)w * 256u + threadIdx.x);
-  const u32 base = hd.x, nd = hd.y;
-  for (u32 t = 64u + threadIdx.x; t < nd; t += 32u * XG_SELL_CW) dict[t] = __ldg(m.dict + (size_t)w * 256u + t);
-  __syncthreads();
-  const unsigned start = startph & 0x55u;
-  const u32 h[8] = { raw.x & 0xFFFFu, raw.x >> 16, raw.y & 0xFFFFu, raw.y >> 16,
-                     raw.z & 0xFFFFu, raw.z >> 16, raw.w & 0xFFFFu, raw.w >> 16 };
-  u32 id[8], prim = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if ((start >> j) & 1u) { prim = base + h[j]; id[j] = prim; }
-    else id[j] = (h[j] == 0xFFFFu) ? XG_NONE : prim + dict[h[j] & 255u];
-  }
-  const uint4 a = make_uint4(id[0], id[1], id[2], id[3]), b = make_uint4(id[4], id[5], id[6], id[7]);
-  sell_lane<T, OP, XM_PLAIN, 1>(f, a, b, startph);
 }
 
 // gs_vec with 3-tuples (a velocity field, BASELINE config 3): a tuple is 3
@@ -509,10 +483,19 @@ __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__device__ __forceinline__ void push_signal_all(const xcu_push &pp)
+// The number of the exchange this launch belongs to (struct xcu_push): read
+// by every thread before any CTA of the launch can have advanced it -- the
+// last CTA to finish does that, and it finishes after every CTA has started.
+__device__ __forceinline__ u32 push_epoch(const xcu_push &pp)
 {
+  return pp.epoch_imm ? pp.epoch_imm : *reinterpret_cast<volatile u32 *>(pp.depoch) + 1u;
+}
+
+__device__ __forceinline__ void push_signal_all(const xcu_push &pp, u32 epoch)
+{
+  *pp.depoch = epoch;
   for (u32 i = 0; i < pp.nsig; ++i)
-    st_release_sys(reinterpret_cast<unsigned *>(pp.sig[i]), pp.epoch);
+    st_release_sys(reinterpret_cast<unsigned *>(pp.sig[i]), epoch);
 }
 
 template <typename T, int OP, int MODE, bool PUSH>
@@ -520,6 +503,8 @@ __global__ void __launch_bounds__(256)
 k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
            unsigned bufvn, int allreduce, xcu_push pp)
 {
+  const u32 epoch = PUSH ? push_epoch(pp) : 0u;
+  const unsigned long long *pbase = PUSH ? pp.base + (size_t)(epoch & 1u) * pp.par_stride : nullptr;
   for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
     u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
     u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
@@ -542,7 +527,7 @@ k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
       if (PUSH) {
         for (u32 s = sb; s < se; ++s) {
           const unsigned nbk = __ldg(pp.snb + s);
-          T *dst = reinterpret_cast<T *>(__ldg(pp.base + nbk));
+          T *dst = reinterpret_cast<T *>(__ldg(pbase + nbk));
           const u32 slot = __ldg(bd.slot[sd] + s) + __ldg(pp.delta + nbk);
           dst[(size_t)slot * bufvn + f.k0 + k] = v;
         }
@@ -562,7 +547,7 @@ k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
       if (done == gridDim.x - 1u) {               // every CTA's stores are out
         *pp.counter = 0u;
         __threadfence_system();
-        push_signal_all(pp);
+        push_signal_all(pp, epoch);
       }
     }
   }
@@ -578,6 +563,8 @@ __global__ void __launch_bounds__(256)
 k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__restrict__ sendbuf,
              unsigned bufvn, xcu_push pp)
 {
+  const u32 epoch = PUSH ? push_epoch(pp) : 0u;
+  const unsigned long long *pbase = PUSH ? pp.base + (size_t)(epoch & 1u) * pp.par_stride : nullptr;
   for (u32 s = blockIdx.x * 256u + threadIdx.x; s < nslots; s += gridDim.x * 256u) {
     const u32 prim = __ldg(sprim + s);
     T *dst = sendbuf;
@@ -585,7 +572,7 @@ k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__res
     if (PUSH) {
       u32 lo = 0, hi = pp.nnb;                    // neighbour whose slot range holds s
       while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (__ldg(pp.start + mid) <= s) lo = mid; else hi = mid; }
-      dst = reinterpret_cast<T *>(__ldg(pp.base + lo));
+      dst = reinterpret_cast<T *>(__ldg(pbase + lo));
       slot = s + __ldg(pp.delta + lo);
     }
     for (unsigned k = 0; k < f.vn; ++k)
@@ -599,7 +586,7 @@ k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__res
       if (done == gridDim.x - 1u) {
         *pp.counter = 0u;
         __threadfence_system();
-        push_signal_all(pp);
+        push_signal_all(pp, epoch);
       }
     }
   }
@@ -608,7 +595,7 @@ k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__res
 // signal without data (a rank whose boundary groups send nothing this call)
 __global__ void k_push_signal(xcu_push pp)
 {
-  if (threadIdx.x == 0) { __threadfence_system(); push_signal_all(pp); }
+  if (threadIdx.x == 0) { const u32 epoch = push_epoch(pp); __threadfence_system(); push_signal_all(pp, epoch); }
 }
 
 // The receiving side of pw_exec_recvs' poll loop (src/gs.upc:409-435): one
@@ -618,10 +605,13 @@ __global__ void k_push_signal(xcu_push pp)
 // peer that never arrives is reported through *status instead of hanging the
 // GPU.
 __global__ void k_push_wait(const unsigned *__restrict__ flags, const u32 *__restrict__ ranks,
-                            u32 n, u32 epoch, unsigned long long timeout_ns, int *status)
+                            u32 n, const u32 *depoch, u32 epoch_imm, unsigned long long timeout_ns, int *status)
 {
   const u32 t = threadIdx.x;
   if (t >= n) return;
+  // my own pack (or signal) kernel precedes this one in stream order and has
+  // stored this exchange's number
+  const u32 epoch = epoch_imm ? epoch_imm : *reinterpret_cast<const volatile u32 *>(depoch);
   const unsigned *f = flags + ranks[t];
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -637,8 +627,11 @@ __global__ void k_push_wait(const unsigned *__restrict__ flags, const u32 *__res
 template <typename T, int OP, int MODE>
 __global__ void __launch_bounds__(256)
 k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ recvbuf,
-             unsigned bufvn, int allreduce)
+             unsigned bufvn, int allreduce, const u32 *depoch, size_t par_bytes)
 {
+  // push transport: the data area of this exchange's parity
+  if (depoch) recvbuf = reinterpret_cast<const T *>(reinterpret_cast<const char *>(recvbuf) +
+                                                    (size_t)(*reinterpret_cast<const volatile u32 *>(depoch) & 1u) * par_bytes);
   for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
     u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
     u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
@@ -672,8 +665,10 @@ k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ re
 template <typename T, int OP>
 __global__ void __launch_bounds__(256)
 k_bnd_unpack_w(xcu_bnd bd, T *__restrict__ u, const T *__restrict__ wgt, int transpose,
-               const T *__restrict__ recvbuf, int allreduce)
+               const T *__restrict__ recvbuf, int allreduce, const u32 *depoch, size_t par_bytes)
 {
+  if (depoch) recvbuf = reinterpret_cast<const T *>(reinterpret_cast<const char *>(recvbuf) +
+                                                    (size_t)(*reinterpret_cast<const volatile u32 *>(depoch) & 1u) * par_bytes);
   for (u32 b = blockIdx.x * 256u + threadIdx.x; b < bd.nb; b += gridDim.x * 256u) {
     u32 gb = __ldg(bd.goff + b), ge = __ldg(bd.goff + b + 1);
     u32 nall = ge - gb, nunf = __ldg(bd.nunf + b), nred, nwr;
@@ -745,19 +740,33 @@ k_csr_scatter(xcu_csr m, FldR<T> out, FldR<T> in)
 // depend on scheduling; it is a different association than the reference's
 // serial loop, hence equal only up to rounding.  HBM-bound: 16 B per element.
 #define DOT_THREADS 256
+#define DOT_UNROLL 4          // independent 16-byte load pairs in flight per thread
 __global__ void __launch_bounds__(DOT_THREADS)
 k_dot_partial(const double *__restrict__ v, const double *__restrict__ w, size_t n, double *__restrict__ part)
 {
   __shared__ double sh[DOT_THREADS];
   const size_t n2 = n / 2, stride = (size_t)gridDim.x * DOT_THREADS;
   const double2 *v2 = reinterpret_cast<const double2 *>(v), *w2 = reinterpret_cast<const double2 *>(w);
-  double acc0 = 0, acc1 = 0;
-  for (size_t i = (size_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n2; i += stride) {
-    const double2 a = __ldg(v2 + i), b = __ldg(w2 + i);
-    acc0 = fma(a.x, b.x, acc0); acc1 = fma(a.y, b.y, acc1);
+  double acc[DOT_UNROLL];
+#pragma unroll
+  for (int q = 0; q < DOT_UNROLL; ++q) acc[q] = 0;
+  size_t i = (size_t)blockIdx.x * DOT_THREADS + threadIdx.x;
+  for (; i + (DOT_UNROLL - 1) * stride < n2; i += DOT_UNROLL * stride) {
+    double2 a[DOT_UNROLL], b[DOT_UNROLL];
+#pragma unroll
+    for (int q = 0; q < DOT_UNROLL; ++q) { a[q] = __ldcs(v2 + i + q * stride); b[q] = __ldcs(w2 + i + q * stride); }
+#pragma unroll
+    for (int q = 0; q < DOT_UNROLL; ++q) acc[q] = fma(a[q].y, b[q].y, fma(a[q].x, b[q].x, acc[q]));
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) acc0 = fma(v[n - 1], w[n - 1], acc0);
-  sh[threadIdx.x] = acc0 + acc1;
+  for (; i < n2; i += stride) {
+    const double2 a = __ldcs(v2 + i), b = __ldcs(w2 + i);
+    acc[0] = fma(a.y, b.y, fma(a.x, b.x, acc[0]));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) acc[0] = fma(v[n - 1], w[n - 1], acc[0]);
+  double t = acc[0];
+#pragma unroll
+  for (int q = 1; q < DOT_UNROLL; ++q) t += acc[q];
+  sh[threadIdx.x] = t;
   __syncthreads();
   for (unsigned s = DOT_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
@@ -941,22 +950,6 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   LAUNCHED();
 }
 
-void xcu_fused_sell_c(void *stream, const xcu_csell *m, const xcu_field *f, int xdom, int xop)
-{
-  if (!m->nblock) return;
-  cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = m->nblock / XG_SELL_CW;
-  const unsigned nthr = 32 * XG_SELL_CW;
-  xcu_field f1 = *f;
-  f1.vn = 1; f1.tuple = 1;
-  const int mode = XM_PLAIN;
-#define X(T, OP, MODE)                                                        \
-  k_fused_sell_c<T, OP, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1))
-  FOR_ALL(X)
-#undef X
-  LAUNCHED();
-}
-
 /* gather-only form for the boundary groups of symmetric maps */
 void xcu_gather_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mode, int xdom, int xop)
 {
@@ -1062,22 +1055,23 @@ void xcu_push_signal(void *stream, const xcu_push *pp)
   LAUNCHED();
 }
 
-void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, u32 epoch,
+void xcu_push_wait(void *stream, const u32 *flags, const u32 *ranks, u32 n, const u32 *depoch, u32 epoch_imm,
                    double timeout_s, int *status)
 {
   if (!n) return;
   k_push_wait<<<1, (n + 31u) & ~31u, 0, (cudaStream_t)stream>>>(
-      flags, ranks, n, epoch, (unsigned long long)(timeout_s * 1e9), status);
+      flags, ranks, n, depoch, epoch_imm, (unsigned long long)(timeout_s * 1e9), status);
   LAUNCHED();
 }
 
 void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode, int xdom,
-                    int xop, int transpose, const void *recvbuf, unsigned bufvn, int allreduce)
+                    int xop, int transpose, const void *recvbuf, unsigned bufvn, int allreduce,
+                    const u32 *depoch, size_t par_bytes)
 {
   if (!b->nb) return;
   cudaStream_t st = (cudaStream_t)stream;
   if (f->w) {
-#define X(T, OP) k_bnd_unpack_w<T, OP><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, (T *)f->p[0], (const T *)f->w, transpose, (const T *)recvbuf, allreduce)
+#define X(T, OP) k_bnd_unpack_w<T, OP><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, (T *)f->p[0], (const T *)f->w, transpose, (const T *)recvbuf, allreduce, depoch, par_bytes)
     FOR_DOM_W(X)
 #undef X
     LAUNCHED();
@@ -1085,7 +1079,7 @@ void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode
   }
 #define X(T, OP, MODE)                                                        \
   k_bnd_unpack<T, OP, MODE><<<bnd_blocks(b->nb), 256, 0, st>>>(               \
-      *b, make_fld<T, MODE>(f), transpose, (const T *)recvbuf, bufvn, allreduce)
+      *b, make_fld<T, MODE>(f), transpose, (const T *)recvbuf, bufvn, allreduce, depoch, par_bytes)
   FOR_ALL(X)
 #undef X
   LAUNCHED();

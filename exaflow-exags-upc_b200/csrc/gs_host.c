@@ -46,9 +46,6 @@ struct gs_data {
   struct xcu_sell d_sell;     /* interior groups, sliced-ELL form (symmetric maps) */
   void *d_sell_mem[3];
   size_t sell_idx_entries;
-  struct xcu_csell d_csell;   /* the same interior map with the compressed index stream
-                                 (experiment, EXAGS_SELL_COMPRESS=1); nblock 0: not in use */
-  void *d_csell_mem[3];
   /* pipelined host-pointer path (np == 1, symmetric map): chunk schedule */
   u32 nwin, *win_min, *win_max;       /* host copies from the sliced layout */
   u32 *h_bidx; size_t h_nbidx;        /* boundary groups' member indices (np > 1) */
@@ -57,7 +54,8 @@ struct gs_data {
   u32 *pipe_run;                      /* [chunks] windows runnable once chunks 0..k are on the device */
   u32 *pipe_out_wave;                 /* [chunks] wave after which chunk j is final */
   void **pipe_ev;                     /* [2*chunks] events */
-  u32 *d_fs; u32 nfs;         /* flagged primaries heading no group, not boundary */
+  u32 nfs;                    /* flagged primaries heading no group, not boundary: one-member groups
+                                 of the interior map (their reduction is the identity gs_init writes) */
   struct xcu_bnd d_bnd;       /* boundary primaries */
   void *d_bnd_mem[20];
   /* push transport (pairwise over peer stores): this handle's mailbox and the
@@ -284,21 +282,27 @@ static void bnd_prepare(struct gs_data *g, struct bnd_ctx *c, unsigned vn, int x
   if (c->push) {
     push_check(g, "before this call");
     push_prepare(g, (size_t)pl->max_total * vn * esz);
+    /* nothing below depends on how many exchanges this mailbox has seen: the
+       exchange number (and with it the parity of the data area) is read from
+       the mailbox header by the kernels, so the same launches can be replayed
+       from a CUDA graph */
     struct xg_mbox *mb = &g->mbox;
-    const u32 M = g->push_nnbmax, epoch = ++mb->epoch, par = epoch & 1u;
+    const u32 M = g->push_nnbmax;
     const int sd = 1 ^ transpose;
     const u64 *t64 = (const u64 *)mb->d_tab;
     const u32 *t32 = (const u32 *)(t64 + 4 * (size_t)M + pl->nsym);
-    c->pp.base = (const unsigned long long *)(t64 + ((size_t)par * 2 + sd) * M);
+    c->pp.base = (const unsigned long long *)(t64 + (size_t)sd * M);
+    c->pp.par_stride = 2 * M;
     c->pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
     c->pp.delta = t32 + (size_t)sd * M;
     c->pp.snb = g->d_snb[sd];
-    c->pp.nsig = pl->nsym; c->pp.epoch = epoch;
-    c->pp.counter = (u32 *)((char *)mb->mine + 512);
+    c->pp.nsig = pl->nsym;
+    c->pp.depoch = (u32 *)((char *)mb->mine + XG_MBOX_EPOCH); c->pp.epoch_imm = 0;
+    c->pp.counter = (u32 *)((char *)mb->mine + XG_MBOX_COUNTER);
     c->push_wait = t32 + 2 * (size_t)M;
     c->pp.start = t32 + 2 * (size_t)M + pl->nsym + (size_t)sd * (M + 1);
     c->pp.nnb = pl->nnb[sd];
-    c->recvbuf = (char *)mb->mine + XG_MBOX_HDR + (size_t)par * mb->data_bytes;
+    c->recvbuf = (char *)mb->mine + XG_MBOX_HDR;          /* parity 0; the unpack adds the parity */
   } else if (xg_world_ipc(w)) {
     c->sendbuf = xg_ipc_buffer(w, (size_t)pl->max_total * vn * 8);
     c->recvbuf = xg_world_scratch(w, c->allred ? 3 : 1, (size_t)pl->max_total * vn * esz);
@@ -358,7 +362,7 @@ static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, 
   struct xg_world *w = g->w;
   const unsigned step = (mode == XM_MANY) ? XG_MAXV : vn;
   if (c->push)
-    xcu_push_wait(scomm, (const u32 *)g->mbox.mine, c->push_wait, g->plan.nsym, c->pp.epoch,
+    xcu_push_wait(scomm, (const u32 *)g->mbox.mine, c->push_wait, g->plan.nsym, c->pp.depoch, 0,
                   push_timeout(), xg_world_push_status(w));
   else if (xg_world_ipc(w)) {
     if (c->allred) exchange_ipc_allreduce(g, c->recvbuf, (size_t)g->plan.total_shared * vn, xd, xop, scomm);
@@ -368,7 +372,8 @@ static void bnd_unpack(struct gs_data *g, struct bnd_ctx *c, void *const *ptrs, 
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 1);
     f.w = wgt;
-    xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, c->recvbuf, vn, c->allred);
+    xcu_bnd_unpack(scomm, &g->d_bnd, &f, mode, xd, xop, transpose, c->recvbuf, vn, c->allred,
+                   c->push ? c->pp.depoch : 0, c->push ? g->mbox.data_bytes : 0);
   }
 }
 
@@ -422,11 +427,8 @@ static void interior_enqueue(struct gs_data *g, void *const *ptrs, int mode, uns
   for (unsigned k0 = 0; k0 < vn; k0 += step) {
     struct xcu_field f; field_of(&f, ptrs, mode, vn, k0, step, 0);
     f.w = wgt;      /* weighted gs: the stores of the group results carry the weight */
-    if (g->d_csell.nblock && !wgt && (mode == XM_PLAIN || f.vn == 1) && xop <= XO_MAX)
-      xcu_fused_sell_c(stream, &g->d_csell, &f, xd, xop);
-    else if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
+    if (g->d_sell.nblock) xcu_fused_sell(stream, &g->d_sell, &f, mode, xd, xop, transpose);
     xcu_fused(stream, &g->d_int.c, &f, mode, xd, xop, transpose);
-    if (!transpose && g->nfs) xcu_init_list(stream, g->d_fs, g->nfs, &f, mode, xd, xop);
   }
 }
 
@@ -580,24 +582,29 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   if (blocking) stream = xg_world_stream(w, 0);   /* async callers own `stream` (0 = legacy default) */
   const size_t esz = xg_dom_bytes(xd), n = g->n;
 
-  void **ptrs = xnew(void *, vn);
+  /* the stream-ordered form is for device-resident data by contract
+     (include/exags_cuda.h): no allocation and no pointer query per call */
+  void *ptrs_few[XG_MAXV];
+  void **ptrs = vn <= XG_MAXV ? ptrs_few : xnew(void *, vn);
   int host = 0;
   if (mode == XM_MANY) {
     void *const *tab = (void *const *)u;
     for (unsigned k = 0; k < vn; ++k) ptrs[k] = tab[k];
-    host = !xcu_is_device_ptr(ptrs[0]);
-    for (unsigned k = 1; k < vn; ++k)
-      if ((!xcu_is_device_ptr(ptrs[k])) != host)
-        xfail("%s: gs_many arrays must be all host or all device", who);
+    if (blocking) {
+      host = !xcu_is_device_ptr(ptrs[0]);
+      for (unsigned k = 1; k < vn; ++k)
+        if ((!xcu_is_device_ptr(ptrs[k])) != host)
+          xfail("%s: gs_many arrays must be all host or all device", who);
+    }
   } else {
     ptrs[0] = u;
-    host = !xcu_is_device_ptr(u);
+    if (blocking) host = !xcu_is_device_ptr(u);
   }
 
   if (!host) {
     gs_enqueue(g, ptrs, mode, vn, xd, op, (int)transpose, stream, 0);
     if (blocking) { xcu_stream_sync(stream); push_check(g, "during this call"); }
-    free(ptrs);
+    if (ptrs != ptrs_few) free(ptrs);
     return;
   }
   /* host data: stage through HBM (still GPU compute) */
@@ -606,7 +613,7 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
     if (!(pp && atoi(pp) == 0)) pipe_plan(g);
     if (g->pipe_chunks) {
       gs_run_host_pipelined(g, ptrs, mode, vn, xd, op, (int)transpose);
-      free(ptrs);
+      if (ptrs != ptrs_few) free(ptrs);
       return;
     }
   }
@@ -623,7 +630,8 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
   else xcu_d2h(u, stage, total, stream);
   xcu_stream_sync(stream);
   push_check(g, "during this call");
-  free(dptr); free(ptrs);
+  free(dptr);
+  if (ptrs != ptrs_few) free(ptrs);
 }
 
 void exags_gs(void *u, gs_dom dom, gs_op_t op, unsigned transpose, struct gs_data *gsh, buffer *buf)
@@ -660,7 +668,7 @@ static void gs_run_weighted(void *u, const void *wgt, int dom, int op, struct gs
   if (!g->on_device)
     xfail("%s: no CUDA device -- this library has no CPU execution path", who);
   if (!g->n) return;
-  if (!xcu_is_device_ptr(u) || !xcu_is_device_ptr(wgt))
+  if (blocking && (!xcu_is_device_ptr(u) || !xcu_is_device_ptr(wgt)))
     xfail("%s: u and w must be device vectors", who);
   if (blocking) stream = xg_world_stream(g->w, 0);
   void *ptrs[1] = { u };
@@ -718,45 +726,6 @@ static int upload_send_primaries(struct gs_data *g, int m)
   return m;
 }
 
-/* EXAGS_SELL_COMPRESS=1 (experiment): a second copy of the interior map with
-   16-bit codes in place of the 32-bit member indices (sell_window.h).  The
-   windows are encoded on the host from the raw layout -- fetched back when the
-   handle was built on the device -- and the plain one-component calls then run
-   k_fused_sell_c.  Maps with flagged members, or with a window the encoding
-   refuses, stay as they are.                                                 */
-static void compress_interior(struct gs_data *g)
-{
-  const char *e = getenv("EXAGS_SELL_COMPRESS");
-  if (!(e && atoi(e)) || !g->on_device || !g->d_sell.nblock || g->d_sell.fmask) return;
-  const u32 nblock = g->d_sell.nblock, nwin = nblock / XG_SELL_WB;
-  u32 *idx = xnew(u32, (size_t)nblock * 256);
-  unsigned char *mask = xnew(unsigned char, (size_t)nblock * 32);
-  xcu_d2h(idx, g->d_sell.idx, (size_t)nblock * 256 * sizeof(u32), 0);
-  xcu_d2h(mask, g->d_sell.mask, (size_t)nblock * 32, 0);
-  xcu_device_sync();
-  unsigned short *code = xnew(unsigned short, (size_t)nblock * 256);
-  u32 *hdr = xnew0(u32, (size_t)nwin * 2), *dict = xnew0(u32, (size_t)nwin * XG_SELL_CDICT);
-  int refused = 0;
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 64) num_threads(xg_setup_threads()) reduction(| : refused)
-#endif
-  for (size_t w = 0; w < nwin; ++w)
-    refused |= xg_sell_compress_window(idx + w * XG_SELL_WSLOTS, mask + w * XG_SELL_LANES,
-                                       code + w * XG_SELL_WSLOTS, dict + w * XG_SELL_CDICT, hdr + w * 2);
-  if (!refused) {
-    g->d_csell_mem[0] = upload(code, (size_t)nblock * 256 * sizeof(unsigned short));
-    g->d_csell_mem[1] = upload(hdr, (size_t)nwin * 2 * sizeof(u32));
-    g->d_csell_mem[2] = upload(dict, (size_t)nwin * XG_SELL_CDICT * sizeof(u32));
-    xcu_device_sync();
-    g->d_csell.nblock = nblock;
-    g->d_csell.mask = g->d_sell.mask;
-    g->d_csell.code = (const unsigned short *)g->d_csell_mem[0];
-    g->d_csell.hdr = (const u32 *)g->d_csell_mem[1];
-    g->d_csell.dict = (const u32 *)g->d_csell_mem[2];
-  }
-  free(idx); free(mask); free(code); free(hdr); free(dict);
-}
-
 static void split_groups(struct gs_data *g, const struct xg_topo *t)
 {
   /* interior CSR = groups (>= 2 members) whose primary is not a boundary
@@ -784,8 +753,8 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     for (size_t gi = GLO(c); gi < GLO(c + 1); ++gi) {
       u32 a = t->gstart[gi], e = t->gstart[gi + 1];
       if (bb < nb && pl->bgrp[bb] == gi) { ++bb; bni_ += e - a; continue; }
-      if (e - a >= 2) { ++ng_; ni_ += e - a; }
-      else if (t->flag[a]) ++nf_;
+      if (e - a >= 2 || t->flag[a]) { ++ng_; ni_ += e - a; }   /* a flagged single is a one-member group */
+      if (e - a < 2 && t->flag[a]) ++nf_;
     }
     cg[c] = ng_; ci[c] = ni_; cf[c] = nf_; cb[c] = lo; cbi[c] = bni_;
   }
@@ -817,12 +786,13 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
         ob += e - a; ++b;
         continue;
       }
-      if (e - a >= 2) {
+      if (e - a >= 2 || t->flag[a]) {
         in.off[og] = (u32)oi;
         if (in.nunf) in.nunf[og] = unf;
         memcpy(in.idx + oi, t->idx + a, (size_t)(e - a) * sizeof(u32));
         oi += e - a; ++og;
-      } else if (t->flag[a]) fs[of++] = t->idx[a];
+      }
+      if (e - a < 2 && t->flag[a]) fs[of++] = t->idx[a];
     }
   }
 #undef GLO
@@ -837,7 +807,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
     xg_sell_build(&sell, &in);
     g->sell_idx_entries = sell.nidx;
   }
-  if (use_sell && !sell.rest.ng && !nfs) {
+  if (use_sell && !sell.rest.ng) {
     /* keep what the pipelined host path needs to schedule windows by chunk */
     g->nwin = sell.nwin;
     g->win_min = sell.win_min; g->win_max = sell.win_max;
@@ -857,7 +827,6 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   }
   if (g->on_device) {
     if (!use_sell) upload_csr(&g->d_int, &in);
-    if (nfs) g->d_fs = (u32 *)upload(fs, nfs * sizeof(u32));
     if (nb) {
       int m = 0;
       struct xcu_bnd *d = &g->d_bnd;
@@ -934,13 +903,14 @@ static double time_exchange(struct gs_data *g, int method)
       const u64 *t64 = (const u64 *)mb->d_tab;
       struct xcu_push pp; memset(&pp, 0, sizeof pp);
       pp.sig = (const unsigned long long *)(t64 + 4 * (size_t)M);
-      pp.nsig = pl->nsym; pp.epoch = epoch;
+      pp.nsig = pl->nsym; pp.epoch_imm = epoch;          /* copies go by the copy engine: parity known here */
+      pp.depoch = (u32 *)((char *)mb->mine + XG_MBOX_EPOCH);
       for (u32 k = 0; k < pl->nnb[1]; ++k)
         xcu_d2d((char *)mb->peer[pl->nb_rank[1][k]] + XG_MBOX_HDR + (size_t)par * mb->data_bytes + (size_t)pl->nb_peer_start[1][k] * 8,
                 (const char *)sb + (size_t)pl->nb_start[1][k] * 8, (size_t)pl->nb_size[1][k] * 8, s);
       xcu_push_signal(s, &pp);
       xcu_push_wait(s, (const u32 *)mb->mine, (const u32 *)(t64 + 4 * (size_t)M + pl->nsym) + 2 * (size_t)M,
-                    pl->nsym, epoch, push_timeout(), xg_world_push_status(w));
+                    pl->nsym, 0, epoch, push_timeout(), xg_world_push_status(w));
     }
     else if (xg_world_ipc(w)) {
       if (method == gs_all_reduce) exchange_ipc_allreduce(g, rb, nsend, XD_F64, XO_ADD, s);
@@ -1004,7 +974,7 @@ static void adopt_interior(struct gs_data *g, const struct xcu_dmap *in, const s
   g->d_int.c.ng = ds.rest.ng; g->d_int.c.ni = ds.rest.ni;
   g->d_int.off = ds.rest.off; g->d_int.idx = ds.rest.idx; g->d_int.nunf = ds.rest.nunf;
   g->d_int.c.off = ds.rest.off; g->d_int.c.idx = ds.rest.idx; g->d_int.c.nunf = ds.rest.nunf;
-  if (ds.nwin && !ds.rest.ng && !g->nfs) {
+  if (ds.nwin && !ds.rest.ng) {
     /* what the pipelined host-pointer path needs to schedule windows by chunk */
     g->nwin = ds.nwin;
     g->win_min = xnew(u32, ds.nwin); g->win_max = xnew(u32, ds.nwin);
@@ -1025,20 +995,22 @@ static void setup_device_np1(struct gs_data *g, const void *id, int idbytes, u32
   double tp[6]; int ntp = 0;
 #define TICK() do { if (prof) { xcu_device_sync(); exags_comm_time(&tp[ntp++]); } } while (0)
   struct xcu_topo dt;
+  struct xcu_dmap in;
   u32 *d_fs = 0;
   TICK();
   xcu_setup_begin();
   xcu_setup_topo(id, idbytes, n, &dt);
   TICK();
-  xcu_setup_local(&dt, &g->d_hall, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
+  xcu_setup_local(&dt, &g->d_hall, &in, &g->d_hfp, &g->nfp, &d_fs, &g->nfs, &g->sectors_f64);
   xcu_setup_topo_free(&dt);
   TICK();
   g->dev_built = 1;
-  g->d_fs = d_fs;
+  xcu_free(d_fs);
   g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;      /* counts now, arrays on demand */
-  /* with one rank the interior map is hall itself; hall stays with the handle
-     for the introspection calls */
-  adopt_interior(g, &g->d_hall, 0);
+  /* with one rank the interior map is hall itself (plus the flagged singles,
+     if any); hall stays with the handle for the introspection calls */
+  adopt_interior(g, in.off ? &in : &g->d_hall, 0);
+  if (in.off) xcu_dmap_free(&in);
   TICK();
   xcu_setup_end();
   g->handle_bytes = sizeof *g + ((size_t)g->d_hall.ng + 1 + g->d_hall.ni + g->nfs + 1) * sizeof(u32);
@@ -1064,7 +1036,7 @@ static void split_groups_device(struct gs_data *g, const struct xcu_topo *dt)
   xcu_setup_split(dt, pl->bgrp, nb, &g->d_hall, &in, &bnd, &bnd2, &g->d_hfp, &g->nfp, &d_fs, &g->nfs,
                   &g->sectors_f64);
   g->dev_built = 1;
-  g->d_fs = d_fs;
+  xcu_free(d_fs);
   g->hall.ng = g->d_hall.ng; g->hall.ni = g->d_hall.ni;
   const u32 ing = in.ng, ini = in.ni, bni = bnd.ni;
   adopt_interior(g, &in, &bnd);
@@ -1163,7 +1135,6 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
   }
   if (dev_maps) {
     setup_device_np1(g, id, idbytes, n, prof);
-    compress_interior(g);
     free(id_own); free(id_staged);
     g->method = method == gs_all_reduce ? gs_all_reduce : gs_pairwise;
     if (verbose && comm->id == 0) {
@@ -1218,7 +1189,6 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
            "sector count %.3f s, exchange plan %.3f s, split + sliced layout + upload %.3f s\n", n,
            tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
 #undef TICK
-  compress_interior(g);
   /* the NCCL communicator is created here, collectively, never lazily inside
      a ncclGroupStart/End bracket */
   if (np > 1) xg_plan_exchange_offsets(&g->plan, w);
@@ -1288,9 +1258,7 @@ void exags_gs_free(struct gs_data *g)
   if (g->on_device) {
     xcu_device_sync();
     xcu_free(g->d_int.off); xcu_free(g->d_int.idx); xcu_free(g->d_int.nunf);
-    xcu_free(g->d_fs);
     for (int m = 0; m < 3; ++m) xcu_free(g->d_sell_mem[m]);
-    for (int m = 0; m < 3; ++m) xcu_free(g->d_csell_mem[m]);
     for (int m = 0; m < 20; ++m) xcu_free(g->d_bnd_mem[m]);
     xcu_free(g->d_brest.off); xcu_free(g->d_brest.idx); xcu_free(g->d_brest.nunf);
     xg_mbox_free(g->w, &g->mbox);

@@ -72,7 +72,8 @@ XG_HD static inline u32 xg_sell_class_order(u32 first, u32 last, const u32 *sg, 
     const u32 a = off[sg[k]];
     if (xg_sell_width(off[sg[k] + 1] - a) != wd) continue;
     if (M == XG_SELL_WSLOTS / 2) break;           /* cannot happen: >= 2 slots each */
-    ck[M] = (unsigned short)(k - first); P[M] = idx[a]; Q[M] = idx[a + 1]; ++M;
+    /* a one-member group (a flagged single) has no second member to order by */
+    ck[M] = (unsigned short)(k - first); P[M] = idx[a]; Q[M] = off[sg[k] + 1] - a > 1 ? idx[a + 1] : idx[a]; ++M;
   }
   const unsigned ls = (chain >> 8) ? (unsigned)(chain >> 8) : 4u;
   const u32 max_twins = (1u << (ls - 3u)) - 1u;
@@ -173,70 +174,6 @@ XG_HD static inline int xg_sell_fill_window(size_t w, u32 first, u32 last, const
     }
   }
   return 0;
-}
-
-/* ---- compressed index stream (experiment, EXAGS_SELL_COMPRESS=1) -----------
-   The member indices are 4 bytes each and 12 % of the hot kernel's DRAM
-   traffic, yet inside a window they are highly regular: the primaries of the
-   256-1024 consecutive groups of a window lie within a few thousand indices of
-   each other, and the other members of a group sit at one of a handful of
-   distances from their primary (the strides to the neighbouring elements: 7
-   distinct values per window on a structured box, < 80 with the elements in
-   random order, tools/compress_study.py).  A window is therefore stored as
-     hdr[2]            base (smallest primary), number of dictionary entries
-     dict[<= 256]      the distinct (member - primary) distances, as uint32
-     code[2048]        16 bits per slot: group start -> primary - base;
-                       other member -> its dictionary index; empty -> 0xFFFF
-   i.e. 2 bytes per slot instead of 4 (the start mask is unchanged).  A window
-   whose primaries span >= 65535 indices or that needs more than 256 distances
-   is not compressible; a handle is compressed only if every window is.
-   Returns 0 when the window was encoded, 1 when it cannot be.                */
-#define XG_SELL_CDICT 256u
-XG_HD static inline int xg_sell_compress_window(const u32 *widx, const unsigned char *wmask,
-                                                unsigned short *code, u32 *dict, u32 *hdr)
-{
-  u32 base = XG_NONE, nd = 0;
-  for (u32 L = 0; L < XG_SELL_LANES; ++L) {
-    const unsigned start = wmask[L] & 0x55u;
-    for (u32 j = 0; j < 8; ++j)
-      if (((start >> j) & 1u) && widx[L * 8 + j] < base) base = widx[L * 8 + j];
-  }
-  if (base == XG_NONE) base = 0;                  /* an empty window */
-  for (u32 L = 0; L < XG_SELL_LANES; ++L) {
-    const unsigned start = wmask[L] & 0x55u;
-    u32 prim = 0;
-    for (u32 j = 0; j < 8; ++j) {
-      const u32 v = widx[L * 8 + j];
-      unsigned short c;
-      if ((start >> j) & 1u) {
-        if (v == XG_NONE || v - base >= 0xFFFFu) return 1;
-        prim = v; c = (unsigned short)(v - base);
-      } else if (v == XG_NONE) c = 0xFFFFu;
-      else {
-        const u32 d = v - prim;                   /* modulo 2^32: members below the primary too */
-        u32 k = 0;
-        while (k < nd && dict[k] != d) ++k;
-        if (k == nd) { if (nd == XG_SELL_CDICT) return 1; dict[nd++] = d; }
-        c = (unsigned short)k;
-      }
-      code[L * 8 + j] = c;
-    }
-  }
-  hdr[0] = base; hdr[1] = nd;
-  return 0;
-}
-
-/* the inverse, as the kernel does it (tests) */
-XG_HD static inline void xg_sell_decompress_lane(const unsigned short *code8, unsigned startmask,
-                                                 const u32 *dict, u32 base, u32 *out8)
-{
-  const unsigned start = startmask & 0x55u;
-  u32 prim = 0;
-  for (u32 j = 0; j < 8; ++j) {
-    const u32 c = code8[j];
-    if ((start >> j) & 1u) { prim = base + c; out8[j] = prim; }
-    else out8[j] = c == 0xFFFFu ? XG_NONE : prim + dict[c & (XG_SELL_CDICT - 1u)];
-  }
 }
 
 #endif

@@ -244,11 +244,11 @@ void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht)
   CU(cudaMemcpy(ht->gstart, dt->gstart, (ngrp + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
 }
 
-void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, u32 **fp, u32 *nfp,
+void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, struct xcu_dmap *in, u32 **fp, u32 *nfp,
                      u32 **fs, u32 *nfs, u64 *sectors)
 {
   Scope sc; CudaBackend &be = sc.be;
-  check(xgsetup::local_maps(be, t, hall, fp, nfp, fs, nfs, sectors), "local maps");
+  check(xgsetup::local_maps(be, t, hall, in, fp, nfp, fs, nfs, sectors), "local maps");
   CU(cudaStreamSynchronize(be.st));
 }
 

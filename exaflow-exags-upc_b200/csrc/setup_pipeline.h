@@ -227,7 +227,10 @@ enum { SEL_ALL2 = 1,      // >= 2 members                                 (hall)
        SEL_BND = 4,       // boundary group, any size                     (boundary CSR)
        SEL_BND2 = 8,      // boundary group with >= 2 members             (boundary sliced map)
        SEL_FP = 16,       // primary flagged                              (flagged_primaries)
-       SEL_FS = 32 };     // primary flagged, single member, not boundary (gs_init list)
+       SEL_FS = 32,       // primary flagged, single member, not boundary (gs_init's part of flagged_primaries)
+       SEL_INTM = 64 };   // SEL_INT2 or SEL_FS: the interior map the kernels run on.  A flagged single is a
+                          // one-member group there: with no unflagged member it reduces to the identity, which
+                          // is what gs_init writes over it (src/gs.upc:1182) -- no separate init pass.
 
 // bgrp: nb boundary groups (device array, may be null when nb == 0)
 template <class B>
@@ -243,8 +246,8 @@ unsigned char *select_groups(B &be, const xcu_topo *t, const u32 *bgrp, u32 nb)
     const u32 a = gstart[k], sz = gstart[k + 1] - a;
     const unsigned bnd = sel[k] & SEL_BND;
     unsigned s = bnd;
-    if (sz >= 2) s |= SEL_ALL2 | (bnd ? SEL_BND2 : SEL_INT2);
-    if (flag[a]) s |= SEL_FP | ((sz == 1 && !bnd) ? SEL_FS : 0u);
+    if (sz >= 2) s |= SEL_ALL2 | (bnd ? SEL_BND2 : (SEL_INT2 | SEL_INTM));
+    if (flag[a]) s |= SEL_FP | ((sz == 1 && !bnd) ? (SEL_FS | SEL_INTM) : 0u);
     sel[k] = (unsigned char)s;
   });
   return sel;
@@ -277,18 +280,22 @@ u64 count_sectors(B &be, size_t n, const xcu_dmap *m)
   return c;
 }
 
-// One rank: hall is also the interior map.
+// One rank: hall is also the interior map, unless there are flagged singles:
+// then `in` is hall plus those as one-member groups (in->off stays null otherwise).
 template <class B>
-int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, u32 **fp, u32 *nfp, u32 **fs, u32 *nfs,
+int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, xcu_dmap *in, u32 **fp, u32 *nfp, u32 **fs, u32 *nfs,
                u64 *sectors)
 {
   *fp = *fs = 0; *nfp = *nfs = 0; *sectors = 0;
+  in->ng = in->ni = 0; in->off = in->idx = in->nunf = 0;
   unsigned char *sel = select_groups(be, t, (const u32 *)0, 0);
-  const int rc = csr_of(be, t, sel, SEL_ALL2, t->any_flag, hall);
+  int rc = csr_of(be, t, sel, SEL_ALL2, t->any_flag, hall);
   if (rc) { be.release(sel); return rc; }
   if (t->any_flag) {
     *nfp = list_of(be, t, sel, SEL_FP, fp);
     *nfs = list_of(be, t, sel, SEL_FS, fs);
+    if (*nfs) rc = csr_of(be, t, sel, SEL_INTM, 1, in);
+    if (rc) { be.release(sel); return rc; }
   }
   be.release(sel);
   *sectors = count_sectors(be, t->n, hall);
@@ -296,7 +303,8 @@ int local_maps(B &be, const xcu_topo *t, xcu_dmap *hall, u32 **fp, u32 *nfp, u32
 }
 
 // Several ranks: the exchange plan has named the boundary groups (bgrp,
-// ascending).  hall as above; in = interior groups with >= 2 members; bnd =
+// ascending).  hall as above; in = interior groups with >= 2 members plus the
+// interior flagged singles as one-member groups; bnd =
 // every boundary group with all its members and unflagged counts; bnd2 = the
 // boundary groups with >= 2 members (built only for maps without flagged
 // labels, where the boundary takes the sliced layout too); fs = flagged single
@@ -310,7 +318,7 @@ int split_maps(B &be, const xcu_topo *t, const u32 *bgrp, u32 nb, xcu_dmap *hall
   bnd2->ng = bnd2->ni = 0; bnd2->off = bnd2->idx = bnd2->nunf = 0;
   unsigned char *sel = select_groups(be, t, bgrp, nb);
   int rc = csr_of(be, t, sel, SEL_ALL2, t->any_flag, hall);
-  if (!rc) rc = csr_of(be, t, sel, SEL_INT2, t->any_flag, in);
+  if (!rc) rc = csr_of(be, t, sel, SEL_INTM, t->any_flag, in);
   if (!rc) rc = csr_of(be, t, sel, SEL_BND, 1, bnd);
   if (!rc && !t->any_flag) rc = csr_of(be, t, sel, SEL_BND2, 0, bnd2);
   if (rc) { be.release(sel); return rc; }

@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     L.exags_comm_scan.argtypes = [vp, comm_ptr, i32, i32, vp, u32, vp]
     L.exags_comm_dot.argtypes = [comm_ptr, vp, vp, u32]
     L.exags_comm_dot.restype = C.c_double
+    L.exags_comm_dot_async.argtypes = [comm_ptr, vp, vp, u32, vp, vp]
+    L.exags_comm_dot_async.restype = None
     L.exags_comm_bcast.argtypes = [comm_ptr, vp, C.c_size_t, u32]
     L.gslib_gs_setup.argtypes = [vp, u32, comm_ptr, i32, i32, i32]
     L.gslib_gs_setup.restype = vp
@@ -258,6 +260,11 @@ def comm_dot(v, w, comm=None) -> float:
     """comm_dot(cp, v, w, n) (src/comm.upc:954): v, w host arrays or device tensors of doubles."""
     n = v.numel() if hasattr(v, "numel") else v.size
     return float(lib().exags_comm_dot(comm if comm is not None else comm_world(), _addr(v), _addr(w), n))
+
+
+def comm_dot_async(v, w, out, stream: int, comm=None) -> None:
+    """Stream-ordered comm_dot (include/exags_cuda.h): out (1 device double) = sum v*w over all ranks."""
+    lib().exags_comm_dot_async(comm if comm is not None else comm_world(), _addr(v), _addr(w), v.numel(), _addr(out), stream)
 
 
 def comm_allreduce(v, dom: int, op: int, comm=None) -> None:

@@ -37,6 +37,15 @@ void exags_gs_weighted(void *u, const void *w, int dom, int op, struct gs_data *
 void exags_gs_weighted_async(void *u, const void *w, int dom, int op,
                              struct gs_data *gsh, void *stream);
 
+/* Stream-ordered comm_dot (src/comm.upc:954-959 on device vectors): *d_out =
+   sum over all ranks of sum_i v[i]*w[i], left in device memory and ordered on
+   `stream`; nothing comes back to the host.  v, w: 16-byte aligned device
+   vectors of n doubles; d_out: one device double.  The summation order is
+   fixed (same bits on every call); with np > 1 the ranks' partial sums are
+   combined by ncclAllReduce on the same stream.                              */
+void exags_comm_dot_async(const comm_ptr comm, const double *v, const double *w,
+                          exags_uint n, double *d_out, void *stream);
+
 /* Device selection (default: LOCAL_RANK mod device count, chosen in
    comm_world).  Must be called before the first comm_world/comm_init.      */
 void exags_set_device(int device);

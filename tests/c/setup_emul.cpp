@@ -97,10 +97,13 @@ extern "C" int setup_emul_split(const void *id, int idbytes, size_t n, const u32
         b_off.push_back((u32)b_idx.size()); b_unf.push_back(unf);
         b_idx.insert(b_idx.end(), ht.idx + a, ht.idx + e);
         if (e - a >= 2) { b2_off.push_back((u32)b2_idx.size()); b2_idx.insert(b2_idx.end(), ht.idx + a, ht.idx + e); }
-      } else if (e - a >= 2) {
-        in_off.push_back((u32)in_idx.size()); in_unf.push_back(unf);
-        in_idx.insert(in_idx.end(), ht.idx + a, ht.idx + e);
-      } else if (ht.flag[a]) fs.push_back(ht.idx[a]);
+      } else {
+        if (e - a >= 2 || ht.flag[a]) {        // a flagged single is a one-member group of the interior map
+          in_off.push_back((u32)in_idx.size()); in_unf.push_back(unf);
+          in_idx.insert(in_idx.end(), ht.idx + a, ht.idx + e);
+        }
+        if (e - a < 2 && ht.flag[a]) fs.push_back(ht.idx[a]);
+      }
     }
     in_off.push_back((u32)in_idx.size()); b_off.push_back((u32)b_idx.size()); b2_off.push_back((u32)b2_idx.size());
   }
@@ -259,6 +262,7 @@ extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int rev
   u64 maxabs = 0;
   int rc = xgsetup::topo_build(be, id, idbytes, n, &dt, &maxabs), out = 0;
   xcu_dmap dh; memset(&dh, 0, sizeof dh);
+  xcu_dmap din; memset(&din, 0, sizeof din);
   xcu_dsell ds; memset(&ds, 0, sizeof ds);
   u32 *dfp = 0, *dfs = 0, dnfp = 0, dnfs = 0;
   u64 sectors = 0;
@@ -271,8 +275,34 @@ extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int rev
   for (size_t g = 0; g < ht.ngrp; ++g)
     for (u32 j = ht.gstart[g]; j < ht.gstart[g + 1]; ++j) if (dt.rowgrp[j] != g) { out = 16; goto done; }
 
-  rc = xgsetup::local_maps(be, &dt, &dh, &dfp, &dnfp, &dfs, &dnfs, &sectors);
+  rc = xgsetup::local_maps(be, &dt, &dh, &din, &dfp, &dnfp, &dfs, &dnfs, &sectors);
   if (rc) { out = 20; goto done; }
+  if ((din.off != 0) != (dnfs != 0)) { out = 25; goto done; }
+  if (din.off) {
+    // hall plus the flagged singles as one-member groups, in group order
+    std::vector<u32> eo, ei, eu;
+    for (size_t g = 0; g < ht.ngrp; ++g) {
+      const u32 a = ht.gstart[g], e = ht.gstart[g + 1];
+      if (e - a < 2 && !ht.flag[a]) continue;
+      u32 unf = 0;
+      for (u32 j = a; j < e && !ht.flag[j]; ++j) ++unf;
+      eo.push_back((u32)ei.size()); eu.push_back(unf);
+      ei.insert(ei.end(), ht.idx + a, ht.idx + e);
+    }
+    eo.push_back((u32)ei.size());
+    if (din.ng + 1 != eo.size() || din.ni != ei.size() || !din.nunf) { out = 26; goto done; }
+    if (!same(din.off, eo.data(), eo.size()) || !same(din.idx, ei.data(), ei.size()) ||
+        !same(din.nunf, eu.data(), eu.size())) { out = 27; goto done; }
+    // and its sliced layout against the host builder's on the same map
+    xg_hmap hin; memset(&hin, 0, sizeof hin);
+    hin.ng = din.ng; hin.ni = din.ni; hin.off = eo.data(); hin.idx = ei.data(); hin.nunf = eu.data();
+    xg_sell hs2; xg_sell_build(&hs2, &hin);
+    xcu_dsell ds2; memset(&ds2, 0, sizeof ds2);
+    rc = xgsetup::sell_build(be, &din, &ds2, xg_sell_pairs_enabled());
+    const int c2 = rc ? 39 : compare_sell(ds2, hs2);
+    xgsetup::sell_release(be, &ds2); xg_sell_free(&hs2);
+    if (c2) { out = 100 + c2; goto done; }
+  }
   if (dh.ng != hh.ng || dh.ni != hh.ni) { out = 21; goto done; }
   if (!same(dh.off, hh.off, (size_t)hh.ng + 1) || !same(dh.idx, hh.idx, hh.ni)) { out = 22; goto done; }
   if ((dh.nunf != 0) != (hh.nunf != 0)) { out = 23; goto done; }
@@ -289,6 +319,7 @@ extern "C" int setup_emul_compare(const void *id, int idbytes, size_t n, int rev
 done:
   xgsetup::sell_release(be, &ds);
   xgsetup::dmap_release(be, &dh);
+  xgsetup::dmap_release(be, &din);
   be.release(dfp); be.release(dfs);
   xgsetup::topo_release(be, &dt);
   xg_sell_free(&hs); xg_hmap_free(&hh); free(hfp); free(hfs); xg_topo_free(&ht);
@@ -313,33 +344,4 @@ extern "C" size_t setup_emul_sell_dump(const void *id, int idbytes, size_t n, u3
   }
   xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
   return nb;
-}
-
-// Compressed index stream (sell_window.h): every window that the encoder
-// accepts must decode back to its raw slots.  Returns the number of windows
-// that are not compressible, or -1 on a decode mismatch.
-extern "C" long setup_emul_compress_roundtrip(const void *id, int idbytes, size_t n)
-{
-  std::vector<i64> wide(n ? n : 1);
-  for (size_t i = 0; i < n; ++i) wide[i] = idbytes == 8 ? ((const i64 *)id)[i] : (i64)((const int *)id)[i];
-  xg_topo ht; xg_topo_build(&ht, wide.data(), n);
-  xg_hmap hh; xg_topo_local_map(&ht, 1, &hh);
-  xg_sell hs; xg_sell_build(&hs, &hh);
-  long refused = 0;
-  std::vector<unsigned short> code(XG_SELL_WSLOTS);
-  std::vector<u32> dict(XG_SELL_CDICT);
-  for (u32 w = 0; w < hs.nwin && refused >= 0; ++w) {
-    const u32 *widx = hs.idx + (size_t)w * XG_SELL_WSLOTS;
-    const unsigned char *wmask = hs.mask + (size_t)w * XG_SELL_LANES;
-    u32 hdr[2];
-    if (xg_sell_compress_window(widx, wmask, code.data(), dict.data(), hdr)) { ++refused; continue; }
-    if (hdr[1] > XG_SELL_CDICT) { refused = -1; break; }
-    for (u32 L = 0; L < XG_SELL_LANES; ++L) {
-      u32 out[8];
-      xg_sell_decompress_lane(code.data() + L * 8, wmask[L], dict.data(), hdr[0], out);
-      if (memcmp(out, widx + L * 8, sizeof out)) { refused = -1; break; }
-    }
-  }
-  xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
-  return refused;
 }

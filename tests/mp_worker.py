@@ -71,7 +71,7 @@ def main():
     unique = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     method = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     rank, np_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    gpu = what in ("exec", "exech", "exec2", "execw")   # exech: host pointers (staged / pipelined path)
+    gpu = what in ("exec", "exech", "exec2", "execw", "execg")   # exech: host pointers (staged / pipelined path)
     if not gpu:
         os.environ["EXAGS_HOST_SETUP_ONLY"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=np_)
@@ -248,6 +248,41 @@ def main():
                         bad = np.flatnonzero(outs[r] != w_r)
                         print(f"MISMATCH execw case={case} {np.dtype(dt).name} {op} rank={r}: {bad.size} differ, first {bad[:5]}")
                         ok = False
+    elif what == "execg":
+        # np > 1 under a CUDA graph (push transport): the exchange number lives in
+        # the mailbox header on the device, so the captured pack / wait / unpack
+        # launches can be replayed; 2 calls captured, 3 replays, against 6 oracle calls
+        for (dt, op, mode, vn) in ((np.float64, "add", 0, 1), (np.int32, "max", 1, 3)):
+            dom, opi = X.NP_DOM[np.dtype(dt)], cases.OPS.index(op)
+            u0 = cases.values(ids.size * vn, dt, op, 300 * rank + 11)
+            dev = torch.from_numpy(u0.copy()).cuda()
+            (X.gs if mode == 0 else lambda *a: X.gs_vec(a[0], vn, *a[1:]))(dev, dom, opi, 0, g)   # warm-up: mailbox, modules
+            dev.copy_(torch.from_numpy(u0))
+            torch.cuda.synchronize()
+            dist.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st = torch.cuda.current_stream().cuda_stream
+                for _ in range(2):
+                    X.gs_async(dev, mode, vn, dom, opi, 0, g, st)
+            dev.copy_(torch.from_numpy(u0))
+            torch.cuda.synchronize()
+            dist.barrier()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            # a plain call after the replays continues the same exchange numbering
+            (X.gs if mode == 0 else lambda *a: X.gs_vec(a[0], vn, *a[1:]))(dev, dom, opi, 0, g)
+            ins, outs = gather_arrays(u0, np_), gather_arrays(dev.cpu().numpy(), np_)
+            if rank == 0:
+                want = [a.copy() for a in ins]
+                for _ in range(7):
+                    orc.exec(want, mode, vn, O.NP_DOM[np.dtype(dt)], opi, 0)
+                for r in range(np_):
+                    if not np.array_equal(outs[r], want[r]):
+                        print(f"MISMATCH execg {np.dtype(dt).name} {op} mode={mode} rank={r}")
+                        ok = False
+            del graph
     elif what == "exec2":
         # two live handles with different neighbour sets, calls interleaved
         # (Nek keeps one handle per mesh): each has its own mailbox and epoch

@@ -542,6 +542,31 @@ def test_weighted_gs_is_dsavg(X):
     X.gs_free(g)
 
 
+def test_comm_dot_async(X):
+    """Stream-ordered comm_dot (include/exags_cuda.h): same bits as the blocking
+    call, result left on the device, capturable in a CUDA graph together with gs."""
+    n = 1_000_003
+    rng = np.random.default_rng(2)
+    a, b = _dev(rng.uniform(-1, 1, n + 1)[:n]), _dev(rng.uniform(-1, 1, n + 1)[:n])
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    X.comm_dot_async(a, b, out, s)
+    torch.cuda.synchronize()
+    assert float(out.item()) == X.comm_dot(a, b)
+    assert abs(float(out.item()) - float(torch.dot(a, b).item())) <= 1e-9 * n ** 0.5
+    ints = _dev(rng.integers(-8, 9, n).astype(np.float64))
+    X.comm_dot_async(ints, ints, out, s)
+    torch.cuda.synchronize()
+    assert float(out.item()) == float((ints * ints).sum().item())      # exact in any order
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        X.comm_dot_async(a, b, out, torch.cuda.current_stream().cuda_stream)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert float(out.item()) == X.comm_dot(a, b)
+
+
 def test_comm_scan_device_vectors(X):
     """comm_scan with device input and output (one rank: empty prefix, own total)."""
     v = torch.tensor([5, -2, 9], dtype=torch.int64, device="cuda")

@@ -138,3 +138,22 @@ def test_weighted_gs_multi_gpu(built, np_, case):
         pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
     codes, outs = run_ranks(np_, [case, "execw", 0, 1], timeout=600)
     assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (3, "blocks")])
+def test_gs_async_under_cuda_graph_one_gpu(built, np_, case):
+    """exags_gs_async with np > 1 captured in a CUDA graph and replayed (push
+    transport; ranks sharing GPU 0): the exchange number is device state."""
+    if _ndev() < 1:
+        pytest.skip("needs a GPU")
+    codes, outs = run_ranks(np_, [case, "execg", 0, 1], timeout=900,
+                            extra_env={"CUDA_VISIBLE_DEVICES": "0", "EXAGS_EXCHANGE": "push"})
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)
+
+
+@pytest.mark.parametrize("np_,case", [(2, "slab"), (4, "blocks"), (8, "blocks")])
+def test_gs_async_under_cuda_graph_multi_gpu(built, np_, case):
+    if _ndev() < np_:
+        pytest.skip(f"needs {np_} GPUs, have {_ndev()}")
+    codes, outs = run_ranks(np_, [case, "execg", 0, 1], timeout=600)
+    assert all(c == 0 for c in codes), f"exit codes {codes}\n" + "\n".join(outs)

@@ -60,13 +60,6 @@ def emul():
         ids = np.ascontiguousarray(ids)
         return L.setup_emul_line_visits(ids.ctypes.data, ids.dtype.itemsize, ids.size)
 
-    L.setup_emul_compress_roundtrip.restype = ctypes.c_long
-    L.setup_emul_compress_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
-
-    def compress(ids):
-        ids = np.ascontiguousarray(ids)
-        return L.setup_emul_compress_roundtrip(ids.ctypes.data, ids.dtype.itemsize, ids.size)
-
     def run(ids, reverse=0):
         ids = np.ascontiguousarray(ids)
         assert ids.dtype in (np.int64, np.int32)
@@ -74,7 +67,6 @@ def emul():
     run.split = split
     run.roundtrip = roundtrip
     run.visits = visits
-    run.compress = compress
     return run
 
 
@@ -175,23 +167,3 @@ def test_pair_ordering_reduces_line_visits(emul, monkeypatch):
     pairs_only = emul.visits(ids)
     monkeypatch.setenv("EXAGS_SELL_PAIRS", "2")
     assert emul.visits(ids) < pairs_only < 0.92 * plain
-
-
-def test_compressed_index_stream_roundtrip(emul):
-    """The 16-bit window encoding of the member indices (sell_window.h,
-    EXAGS_SELL_COMPRESS): every window of a SEM box is accepted and decodes back
-    to its raw slots, also with the elements in random order; label sets without
-    that regularity are refused window by window (and then stay uncompressed),
-    never decoded wrongly."""
-    for dims in [(2, 2, 2, 3), (16, 16, 6, 7), (7, 5, 3, 9), (40, 1, 1, 7)]:
-        assert emul.compress(semmesh.box_ids(*dims)) == 0, dims
-    ids = semmesh.box_ids(10, 9, 6, 7).reshape(-1, 512)
-    ids = ids[np.random.default_rng(3).permutation(ids.shape[0])].reshape(-1)
-    assert emul.compress(ids) == 0
-    flagged = semmesh.box_ids(6, 6, 4, 5).copy()
-    flagged[::5] = -flagged[::5]
-    assert emul.compress(flagged) >= 0
-    for seed in range(4):
-        rnd = cases.random_ids(6000 + 500 * seed, 1200, 80 + seed, long_group=20)
-        assert emul.compress(rnd) >= 0            # may refuse windows, must never mis-decode
-    assert emul.compress(np.zeros(0, np.int64)) == 0

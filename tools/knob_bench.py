@@ -1,7 +1,6 @@
 """A/B timing on M7 of the layout knobs that are read at gs_setup time, one handle per setting,
 interleaved so that drift hits every setting alike:  python tools/knob_bench.py
-    EXAGS_SELL_LINE_SHIFT=5   chain ordering on 32-element lines (the line of a 4-byte field)
-    EXAGS_SELL_COMPRESS=1     16-bit index stream (k_fused_sell_c)
+    EXAGS_SELL_LINE_SHIFT=4|5|6   chain ordering on 16/32/64-element lines
 for gs(add) on double, float, and gs_vec(3, float)."""
 import json
 import os
@@ -20,7 +19,7 @@ except Exception:
     pass
 ids = semmesh.box_ids(64, 64, 48, 7)
 n = ids.size
-KNOBS = ("EXAGS_SELL_LINE_SHIFT", "EXAGS_SELL_COMPRESS")
+KNOBS = ("EXAGS_SELL_LINE_SHIFT", "EXAGS_SELL_PIPE")
 
 
 def handle(**env):
@@ -33,9 +32,9 @@ def handle(**env):
     return g
 
 
-H = {"default": handle(), "line_shift=5": handle(EXAGS_SELL_LINE_SHIFT=5), "compress": handle(EXAGS_SELL_COMPRESS=1),
-     "compress+line_shift=5": handle(EXAGS_SELL_COMPRESS=1, EXAGS_SELL_LINE_SHIFT=5)}
-info = H["default"].info()
+H = {"line_shift=4": handle(EXAGS_SELL_LINE_SHIFT=4), "line_shift=5": handle(EXAGS_SELL_LINE_SHIFT=5),
+     "line_shift=6": handle(EXAGS_SELL_LINE_SHIFT=6)}
+info = H["line_shift=5"].info()
 G, S, nsec = info["groups"], info["members"], info["sectors_f64"]
 stream = torch.cuda.current_stream().cuda_stream
 for label, mode, vn, dom, dt in (("gs(add,double)", X.mode_plain, 1, X.gs_double, torch.float64),
@@ -49,8 +48,6 @@ for label, mode, vn, dom, dt in (("gs(add,double)", X.mode_plain, 1, X.gs_double
     best = {}
     for rep in range(3):
         for name, g in H.items():
-            if "compress" in name and vn != 1:
-                continue
             for _ in range(3):
                 X.gs_async(u, mode, vn, dom, X.gs_add if dt.is_floating_point else X.gs_max, 0, g, stream)
             torch.cuda.synchronize()

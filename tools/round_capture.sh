@@ -14,7 +14,6 @@ python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.txt 2>&1; echo "pytest rc=$
 python bench.py --steps 20 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; rc=$?; echo "bench rc=$rc"; cat $O/bench_$TAG.json
 timeout 300 python tools/configs_bench.py > $O/configs_$TAG.txt 2>&1; cat $O/configs_$TAG.txt
 timeout 120 python tools/weighted_bench.py > $O/weighted_$TAG.txt 2>&1; cat $O/weighted_$TAG.txt
-timeout 300 python tools/compress_check.py > $O/compress_$TAG.txt 2>&1; echo "compress check rc=$?"; cat $O/compress_$TAG.txt
 if [ $rc = 0 ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_${TAG}_a.log 2>&1
