@@ -334,6 +334,38 @@ def run_gpu(args) -> None:
            "ms_per_step": e2e_ms, "steps": e2e_steps,
            "api": "gs(u_host, gs_double, gs_add, 0, gsh, NULL) on pinned host memory"}
 
+    # ---- the same call on an ordinary (pageable) host array, as a reference caller passes it
+    #      (src/gs.upc:1187-1191): as it comes, and page-locked once by the library
+    #      (EXAGS_HOST_REGISTER / exags_host_register, csrc/gs_host.c) -------------------------
+    pg = {}
+    pbuf = np.empty(n, dtype=np.float64)
+    for label, register in (("driver_staged", False), ("registered", True)):
+        if register:
+            X.lib().exags_host_register.argtypes = [X.C.c_void_p, X.C.c_size_t]
+            X.lib().exags_host_register.restype = X.C.c_int
+            X.lib().exags_host_unregister.argtypes = [X.C.c_void_p]
+            t_reg0 = time.perf_counter()
+            ok_reg = X.lib().exags_host_register(pbuf.ctypes.data, pbuf.nbytes)
+            t_reg = time.perf_counter() - t_reg0
+        np.copyto(pbuf, host.numpy())
+        X.gs(pbuf, X.gs_double, X.gs_add, 0, g)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(3):
+            X.gs(pbuf, X.gs_double, X.gs_add, 0, g)
+        barrier()
+        ms = 1e3 * (time.perf_counter() - w0) / 3
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        pg[label] = {"value": n * world / (ms * 1e-3) / 1e9, "ms_per_step": ms, "steps": 3}
+        if register:
+            pg[label].update({"register_s": t_reg, "register_ok": bool(ok_reg)})
+            X.lib().exags_host_unregister(pbuf.ctypes.data)
+    del pbuf
+    e2e["pageable"] = pg
+
     # ---- roofline of the dominant kernel (the fused interior kernel) ----
     peak, peak_src = hbm_peak()
     G, S, nsec = info["groups"], info["members"], info["sectors_f64"]

@@ -185,6 +185,9 @@ void *xg_host_alltoallv(struct xg_world *w, const void *rows, size_t rowbytes,
                         const size_t *sendcnt, size_t *recvcnt, size_t *nrecv);
 
 /* ---- CUDA side (gs_cuda.cu), thin C ABI used by the host C code ---------- */
+int    xcu_ptr_kind(const void *p);                 /* 0 pageable host, 1 pinned/registered host, 2 device */
+int    xcu_host_register(void *p, size_t bytes);    /* 1 on success */
+void   xcu_host_unregister(void *p);
 int    xcu_device_count(void);
 int    xcu_set_device(int dev);
 void  *xcu_malloc(size_t bytes);

@@ -259,7 +259,14 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) if (id0[j] != XG_NONE) mem |= 1u << j;
   unsigned in = mem, out = mem;               // slots that contribute / are written
-  if (FLG) { if (transpose) out = mem & (~flg | start); else in = mem & ~flg; }
+  if (FLG) {
+    if (transpose) {
+      // a one-member group (a flagged single: a start bit with the next slot
+      // empty) only exists for gs_init, which runs with transpose == 0: skip it
+      mem &= ~(start & ~(mem >> 1));
+      in = mem; out = mem & (~flg | start);
+    } else in = mem & ~flg;
+  }
   if (GONLY) out &= start;
   // everything below addresses memory in "fetch order": id[], lin, lout
   u32 id[8];
@@ -399,16 +406,10 @@ template <> struct Pair<float>     { typedef float2 type; };
 template <> struct Pair<int>       { typedef int2 type; };
 template <> struct Pair<long long> { typedef longlong2 type; };
 
-template <typename T, int OP, int MINB>
-__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
-k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
+template <typename T, int OP>
+__device__ __forceinline__ void vec3_lane(T *__restrict__ u, const uint4 a, const uint4 b, const unsigned startph)
 {
   typedef typename Pair<T>::type T2;
-  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
-  const unsigned lane = threadIdx.x & 31u;
-  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
-  const uint4 a = __ldg(p), b = __ldg(p + 1);
-  const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
   const unsigned start = startph & 0x55u, ph = startph & 0xAAu;   // see swap_pair_bits
   const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   u32 id[8];                                   // fetch order
@@ -461,6 +462,30 @@ k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
       u[base + (odd ? 0 : 2)] = odd ? x[0][j] : x[2][j];
     }
 }
+
+template <typename T, int OP, int MINB>
+__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
+{
+  const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint4 *p = reinterpret_cast<const uint4 *>(m.idx + ((size_t)c * 32u + lane) * 8u);
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  const unsigned startph = __ldg(m.mask + (size_t)c * 32u + lane);
+  vec3_lane<T, OP>(u, a, b, startph);
+}
+
+// A persistent form of these kernels -- CTAs that stay resident and walk the
+// windows round robin while one thread streams the index blocks of the windows
+// ahead into a shared-memory ring with TMA bulk copies (cp.async.bulk +
+// mbarrier), so that no warp waits a memory latency for its indices -- was
+// built and measured in round 2 and is not kept: 0.402 ms against 0.321 ms with
+// a 2-stage ring, 0.548 ms with 4 stages.  The ring takes its shared memory
+// out of the L1 (17 KB x 6 CTAs per stage pair), the L1 hit rate of the field
+// accesses falls from 42 % to 30 %, and the field's lines -- which this layout
+// arranges to be shared between the loads of a warp and of its neighbours --
+// are what the L1 is needed for (profiles/r2_knobs_pipe_line_shift.txt,
+// profiles/r2_ncu_persistent_tma_kernels_summary.txt).
 
 template <typename T, int OP, int MODE>
 __global__ void __launch_bounds__(256)
@@ -1193,6 +1218,23 @@ int xcu_is_device_ptr(const void *p)
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+
+/* 0: pageable host memory, 1: pinned or registered host memory, 2: device / managed */
+int xcu_ptr_kind(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 2;
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+/* page-lock a caller's array so that copies run at link speed and overlap
+   (non-fatal: 0 when the driver refuses, e.g. over the locked-memory limit)   */
+int xcu_host_register(void *p, size_t bytes)
+{
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return 1;
+}
+void xcu_host_unregister(void *p) { if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError(); }
 
 void *xcu_stream_create(int high_priority)
 {

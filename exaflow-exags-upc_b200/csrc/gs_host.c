@@ -24,6 +24,7 @@
 
 struct dev_csr { struct xcu_csr c; u32 *off, *idx, *nunf; };
 
+
 struct gs_data {
   comm_ptr comm;
   struct xg_world *w;
@@ -568,6 +569,47 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
   push_check(g, "during this call");
 }
 
+/* Pageable host arrays.  The reference's u is an ordinary host array
+   (src/gs.upc:1187-1191; Nek passes Fortran arrays from static storage).  A
+   cudaMemcpyAsync on pageable memory is staged by the driver through its own
+   small pinned buffers and does not overlap; page-locking the caller's array
+   once (cudaHostRegister) lifts it to the speed of pinned memory for every
+   later call.  A registration must not outlive the array -- memory that is
+   freed while registered and mapped again at the same address would be copied
+   from its old pages -- so the library never registers on its own by default:
+     EXAGS_HOST_REGISTER=1   register an array the second time gs() sees it
+                             (same address and size; >= 1 MB), keep it;
+     EXAGS_HOST_REGISTER=2   register on first sight;
+     exags_host_register / exags_host_unregister (include/exags_cuda.h) for
+                             callers that manage it themselves.
+   Callers that keep their fields for the length of the run (Nek5000 does) can
+   switch it on safely.                                                       */
+#define XG_HOSTREG_MAX 64
+static struct { void *p; size_t bytes; unsigned seen; int registered; } g_hostreg[XG_HOSTREG_MAX];
+static int g_hostreg_n = 0, g_hostreg_mode = 0;
+
+static void hostreg_note(void *p, size_t bytes)
+{
+  { const char *e = getenv("EXAGS_HOST_REGISTER"); g_hostreg_mode = e ? atoi(e) : 0; }
+  if (g_hostreg_mode <= 0 || bytes < ((size_t)1 << 20) || xcu_ptr_kind(p) != 0) return;
+  int k = 0;
+  while (k < g_hostreg_n && !(g_hostreg[k].p == p && g_hostreg[k].bytes == bytes)) ++k;
+  if (k == g_hostreg_n) {
+    if (g_hostreg_n == XG_HOSTREG_MAX) return;
+    g_hostreg[k].p = p; g_hostreg[k].bytes = bytes; g_hostreg[k].seen = 0; g_hostreg[k].registered = 0;
+    ++g_hostreg_n;
+  }
+  if (++g_hostreg[k].seen >= (g_hostreg_mode >= 2 ? 1u : 2u) && !g_hostreg[k].registered)
+    g_hostreg[k].registered = xcu_host_register(p, bytes) ? 1 : -1;     /* -1: refused, do not retry */
+}
+
+int exags_host_register(void *p, size_t bytes) { xg_world_get(); return xcu_host_register(p, bytes); }
+void exags_host_unregister(void *p)
+{
+  for (int k = 0; k < g_hostreg_n; ++k) if (g_hostreg[k].p == p) g_hostreg[k] = g_hostreg[--g_hostreg_n];
+  xcu_host_unregister(p);
+}
+
 static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned transpose,
                    struct gs_data *g, void *stream, int blocking, const char *who)
 {
@@ -608,6 +650,8 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
     return;
   }
   /* host data: stage through HBM (still GPU compute) */
+  if (mode == XM_MANY) for (unsigned k = 0; k < vn; ++k) hostreg_note(ptrs[k], n * esz);
+  else hostreg_note(u, n * esz * vn);
   if (g->nwin && !(mode == XM_MANY && vn > XG_MAXV)) {
     const char *pp = getenv("EXAGS_HOST_PIPELINE");
     if (!(pp && atoi(pp) == 0)) pipe_plan(g);
@@ -816,7 +860,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
-    g->d_sell.nblock = sell.nblock;
+      g->d_sell.nblock = sell.nblock;
     g->d_sell_mem[0] = upload(sell.mask, (size_t)sell.nblock * 32 + 1);
     g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
     g->d_sell.mask = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
@@ -869,7 +913,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   } else {
     g->d_int.c.ng = in.ng; g->d_int.c.ni = in.ni;
   }
-  g->handle_bytes += ((size_t)ng + 1 + ni + nfs + nb + 1 + bni + nb) * sizeof(u32);
+  g->handle_bytes += ((size_t)ng + 1 + ni - nfs + nb + 1 + bni + nb) * sizeof(u32);   /* ng, ni count the flagged singles too */
   xg_sell_free(&sell);
   xg_hmap_free(&in); free(fs); free(bgoff); free(bgidx); free(bnunf);
 }
@@ -1068,7 +1112,7 @@ static void split_groups_device(struct gs_data *g, const struct xcu_topo *dt)
   } else xcu_dmap_free(&bnd);
   xcu_dmap_free(&bnd2);
   xcu_device_sync();
-  g->handle_bytes += ((size_t)ing + 1 + ini + g->nfs + nb + 1 + bni + nb) * sizeof(u32);
+  g->handle_bytes += ((size_t)ing + 1 + ini - g->nfs + nb + 1 + bni + nb) * sizeof(u32);
 }
 
 /* host copies of a device-built handle's group map, for the introspection calls */

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) k_setup_for_each(size_t n, F f)
 namespace {
 
 // One backend per process, created on first use and never destroyed (its
-// members would outlive the CUDA context at exit).  Work arrays come from the
-// device's stream-ordered memory pool: between begin() and end() the pool
+// members would outlive the CUDA context at exit).  Work arrays come from a
+// stream-ordered memory pool of the library's own: between begin() and end() the pool
 // keeps what the passes free, so the ~40 arrays of one gs_setup reuse each
 // other's memory instead of going to the driver; end() hands everything that
 // is not part of the finished handle back.  Arrays that survive (the maps of
@@ -52,8 +52,8 @@ struct CudaBackend {
   int sms = 148;
   int dev = -1;
   int depth = 0;
-  cudaMemPool_t pool = nullptr;
-  unsigned long long saved_threshold = 0;
+  cudaMemPool_t pool = nullptr;   // the library's own pool (not the device's default one)
+  bool pool_own = false;
 
   void begin()
   {
@@ -61,18 +61,29 @@ struct CudaBackend {
     int d = 0;
     CU(cudaGetDevice(&d));
     if (d != dev) {
+      /* a memory pool and a stream of the library's own, per device: gs_setup
+         neither trims nor re-tunes the application's default pool, and its
+         passes do not run on the legacy default stream.  The stream is a
+         blocking one, so labels the caller produced on the default stream are
+         ordered before the first pass without an explicit synchronisation.   */
+      if (res) { cudaFree(res); res = nullptr; }
+      if (pool_own) { cudaStreamDestroy(st); cudaMemPoolDestroy(pool); pool_own = false; }
       dev = d;
       CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-      res = nullptr;              // per-device; the few bytes of a previous device stay behind
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof props);
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      CU(cudaMemPoolCreate(&pool, &props));
+      unsigned long long keep = ~0ull;             // freed blocks stay for the passes that follow
+      CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      CU(cudaStreamCreateWithFlags(&st, cudaStreamDefault));
+      pool_own = true;
       if (!res_h) CU(cudaMallocHost(&res_h, 64));
     }
     if (!res) CU(cudaMalloc(&res, 64));
-    /* keep freed blocks for the length of the setup; the application's own
-       setting comes back in end() */
-    unsigned long long keep = ~0ull;
-    CU(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &saved_threshold));
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   void end()
   {
@@ -80,8 +91,7 @@ struct CudaBackend {
     CU(cudaStreamSynchronize(st));
     if (tmp) { CU(cudaFreeAsync(tmp, st)); tmp = nullptr; tmp_bytes = 0; }
     CU(cudaStreamSynchronize(st));
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &saved_threshold));
-    CU(cudaMemPoolTrimTo(pool, (size_t)saved_threshold));
+    CU(cudaMemPoolTrimTo(pool, 0));                // what the handle keeps stays allocated; the rest goes back
     xcu_note_launches(launches);
     launches = 0;
   }
@@ -89,7 +99,7 @@ struct CudaBackend {
   template <class T> T *alloc(size_t count)
   {
     void *p = nullptr;
-    CU(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st));
+    CU(cudaMallocFromPoolAsync(&p, (count ? count : 1) * sizeof(T), pool, st));
     return (T *)p;
   }
   void release(void *p)
@@ -114,7 +124,7 @@ struct CudaBackend {
   {
     if (bytes <= tmp_bytes) return;
     if (tmp) CU(cudaFreeAsync(tmp, st));
-    CU(cudaMallocAsync(&tmp, bytes, st));
+    CU(cudaMallocFromPoolAsync(&tmp, bytes, pool, st));
     tmp_bytes = bytes;
   }
   void sort_pairs(u64 *&k, u64 *&k2, u32 *&v, u32 *&v2, size_t n, unsigned bits)

@@ -82,6 +82,12 @@ void  exags_memcpy_h2d(void *dst, const void *src, size_t bytes);
 void  exags_memcpy_d2h(void *dst, const void *src, size_t bytes);
 void  exags_device_sync(void);
 void *exags_host_malloc_pinned(size_t bytes);
+/* Page-lock / release an ordinary host array that gs() will be called on, so
+   that its copies run at link speed (cudaHostRegister).  The array must be
+   unregistered before it is freed.  EXAGS_HOST_REGISTER=1|2 makes gs() do this
+   itself for arrays it sees repeatedly.  Returns 1 on success. */
+int   exags_host_register(void *p, size_t bytes);
+void  exags_host_unregister(void *p);
 void  exags_host_free_pinned(void *p);
 
 #ifdef __cplusplus

@@ -71,8 +71,11 @@ def sector_counts(handle, esz, vn_tuple, transpose):
         return s, s, full.numel(), G, 0
     fp = torch.from_numpy(handle.dump_map(2).astype(np.int64)).cuda()
     fp = fp[fp != NIL]
-    rd, wr = (unf, torch.cat([full, fp])) if not transpose else (full, unf)
-    return nsec(rd), nsec(wr), full.numel(), G, info["flagged_singles"]
+    # a store into a sector makes DRAM read it first (32-byte ECC granularity) unless the whole sector is
+    # written, so the sectors read are those of every member touched at all; written: those of the stored ones
+    touched = torch.cat([full, fp])
+    wr = touched if not transpose else unf
+    return nsec(touched), nsec(wr), full.numel(), G, info["flagged_singles"]
 
 
 def run(name, mode, vn, dom, op, handle, transpose=0, weighted=False, secs=None):
@@ -112,9 +115,19 @@ def run(name, mode, vn, dom, op, handle, transpose=0, weighted=False, secs=None)
     if key not in SEC:
         SEC[key] = sector_counts(handle, esz, tuple_, transpose)
     rd, wr, S, G, nfs = SEC[key]
-    b_alg = 32 * (rd + wr) * comps + 4 * S + 4 * (G + 1) + (esz * S if weighted else 0) + 4 * nfs
-    print(f"{name:46s} {ms:8.4f} ms  {n / ms / 1e6:8.1f} GDOF/s  B_alg {b_alg / n:6.2f} B/DOF  "
-          f"{b_alg / ms / 1e6:7.0f} GB/s  frac {b_alg / ms / 1e6 / peak:.3f}", flush=True)
+    extra = (esz * S if weighted else 0) + 4 * nfs
+    b_sec = 32 * (rd + wr) * comps + 4 * S + 4 * (G + 1) + extra
+    # SURVEY.md 8d's per-unit figure ("every sector is touched": 2*vn*sizeof(T)*n + 4S + 4(G+1), with the
+    # library's own count of touched sectors of a double field scaled to the element size); for gs_vec tuples
+    # that over-counts -- 43 % of the DOFs are no members and a 24-byte tuple leaves whole sectors untouched --
+    # so the count from the map is printed beside it
+    sec_f64 = handle.info()["sectors_f64"]
+    vtot = vn if mode != X.mode_plain else 1
+    b_svy = 2 * 32 * (sec_f64 * esz * vtot / 8.0 if esz * vtot >= 8 else sec_f64 / 2.0) + 4 * S + 4 * (G + 1) + extra
+    sym = rd == wr
+    print(f"{name:42s} {ms:8.4f} ms {n / ms / 1e6:7.1f} GDOF/s | SURVEY 8d bytes {b_svy / n:6.2f} B/DOF frac "
+          f"{(b_svy / ms / 1e6 / peak if sym else float('nan')):.3f} | sectors from the map {b_sec / n:6.2f} B/DOF "
+          f"frac {b_sec / ms / 1e6 / peak:.3f}", flush=True)
 
 
 SEC = {}
