@@ -90,6 +90,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def nvlink_kib(index: int):
+    """(tx, rx) payload KiB this GPU has moved over all its NVLink links so far -- the
+    driver's hardware counters (NVML field values NVLINK_THROUGHPUT_DATA_TX/RX, scope = every
+    link), or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber: go through the UUID of the torch device
+        import torch
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = None
+        for k in range(pynvml.nvmlDeviceGetCount()):
+            hk = pynvml.nvmlDeviceGetHandleByIndex(k)
+            u = pynvml.nvmlDeviceGetUUID(hk)
+            u = u.decode() if isinstance(u, bytes) else u
+            if uuid in u:
+                h = hk
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        all_links = 0xFFFFFFFF
+        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, all_links),
+                                                 (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, all_links)])
+        if any(x.nvmlReturn != 0 for x in v):
+            return None
+        return int(v[0].value.ullVal), int(v[1].value.ullVal)
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------
 #  CPU arm: the oracle (port of the reference algorithm) on the host cores
 # --------------------------------------------------------------------------
@@ -297,12 +326,14 @@ def run_gpu(args) -> None:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = X.kernel_launches()
+    nvl0 = nvlink_kib(local) if world > 1 else None
     barrier()
     ev[0].record()
     for k in range(args.steps):
         step()
         ev[k + 1].record()
     barrier()
+    nvl1 = nvlink_kib(local) if world > 1 else None
     launches = X.kernel_launches() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
@@ -335,11 +366,12 @@ def run_gpu(args) -> None:
            "api": "gs(u_host, gs_double, gs_add, 0, gsh, NULL) on pinned host memory"}
 
     # ---- the same call on an ordinary (pageable) host array, as a reference caller passes it
-    #      (src/gs.upc:1187-1191): as it comes, and page-locked once by the library
-    #      (EXAGS_HOST_REGISTER / exags_host_register, csrc/gs_host.c) -------------------------
+    #      (src/gs.upc:1187-1191): as it comes (the library moves it through pinned bounce rings
+    #      with the host cores), and page-locked once (EXAGS_HOST_REGISTER / exags_host_register,
+    #      csrc/gs_host.c) ------------------------------------------------------------------------
     pg = {}
     pbuf = np.empty(n, dtype=np.float64)
-    for label, register in (("driver_staged", False), ("registered", True)):
+    for label, register in (("bounce_rings", False), ("registered", True)):
         if register:
             X.lib().exags_host_register.argtypes = [X.C.c_void_p, X.C.c_size_t]
             X.lib().exags_host_register.restype = X.C.c_int
@@ -402,6 +434,18 @@ def run_gpu(args) -> None:
                 cb = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception as exc:
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"cpu baseline failed: {exc}"}
+        nvlink = None
+        if nvl0 is not None and nvl1 is not None:
+            # rank 0's GPU over the timed region (it also carries the barrier's few bytes of NCCL traffic);
+            # the exchange occupies the link for the length of the pack kernel, a few tens of microseconds
+            # per call, so the per-call average against 900 GB/s per direction is a small number by design
+            tx, rx = (nvl1[0] - nvl0[0]) * 1024 / args.steps, (nvl1[1] - nvl0[1]) * 1024 / args.steps
+            nvlink = {"source": "NVML field values NVLINK_THROUGHPUT_DATA_TX/RX, all links of rank 0's GPU, "
+                                "difference over the timed steps",
+                      "tx_bytes_per_step": tx, "rx_bytes_per_step": rx,
+                      "expected_payload_bytes_per_step": 8 * info["send_slots"],
+                      "avg_GBps_per_direction_over_step": tx / (ms_per_step * 1e-3) / 1e9,
+                      "peak_GBps_per_direction": 900.0}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -414,7 +458,7 @@ def run_gpu(args) -> None:
                            "setup_s": t_setup, "method": "pairwise", "exchange": transport,
                            "halo_bytes_sent_per_rank_per_step": 8 * info["send_slots"]},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cb, "check": check}
+                "roofline": roofline, "cpu_baseline": cb, "check": check, "nvlink": nvlink}
         print(json.dumps(line), flush=True)
     X.gs_free(g)
     if dist is not None:

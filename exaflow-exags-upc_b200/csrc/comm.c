@@ -24,6 +24,7 @@
 #include <fcntl.h>
 #include <sched.h>
 #include <stdatomic.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,6 +48,11 @@ struct xw_ctl {
   _Atomic unsigned attached;
   _Atomic unsigned bar_count;
   _Atomic unsigned bar_sense;
+  /* who is attached: a rank that waits long looks whether the others are still
+     alive, and a late rank can tell a segment left behind by a killed run
+     (its owner, rank 0, is gone) from the one this launch created */
+  int pid[XW_MAXNP];
+  unsigned long long owner_start;     /* start time of rank 0's process (/proc/<pid>/stat field 22) */
   unsigned long long pub_bytes[XW_MAXNP];
   char small[XW_MAXNP][XW_SMALL];
 };
@@ -100,25 +106,69 @@ static void relax(unsigned *spins)
   nanosleep(&ts, 0);
 }
 
+/* start time of a process in clock ticks since boot (0 when it does not exist) */
+static unsigned long long proc_start_time(int pid)
+{
+  unsigned long long start = 0;
+  char path[64], line[1024];
+  snprintf(path, sizeof path, "/proc/%d/stat", pid);
+  FILE *f = fopen(path, "r");
+  if (!f) return 0;
+  if (fgets(line, sizeof line, f)) {
+    char *p = strrchr(line, ')');
+    int field = 2;
+    while (p && *p && field < 22) { if (*p == ' ') ++field; ++p; }
+    if (p) start = strtoull(p, 0, 10);
+  }
+  fclose(f);
+  return start;
+}
+
+/* 0 when the process has ended (a zombie waiting to be reaped counts as ended) */
+static int proc_alive(int pid)
+{
+  char path[64], line[512];
+  snprintf(path, sizeof path, "/proc/%d/stat", pid);
+  FILE *f = fopen(path, "r");
+  if (!f) return kill(pid, 0) == 0 || errno != ESRCH;     /* no /proc: fall back to the signal probe */
+  int alive = 1;
+  if (fgets(line, sizeof line, f)) {
+    const char *p = strrchr(line, ')');
+    if (p && p[1] == ' ' && (p[2] == 'Z' || p[2] == 'X')) alive = 0;
+  }
+  fclose(f);
+  return alive;
+}
+
+static double host_timeout(void)
+{
+  static double t = -1;
+  if (t < 0) { const char *v = getenv("EXAGS_HOST_TIMEOUT_S"); t = v && atof(v) > 0 ? atof(v) : 1800.0; }
+  return t;
+}
+
+/* Called now and then from a wait loop of the rendezvous: a peer that died
+   (exags_fail, a signal) ends the wait with the reference's fail() instead of a
+   hang, and no wait lasts longer than EXAGS_HOST_TIMEOUT_S (default 1800 s).  */
+static void wait_check(struct xg_world *w, double t0, const char *what)
+{
+  double now; exags_comm_time(&now);
+  for (int p = 0; p < w->np; ++p) {
+    const int pid = w->ctl->pid[p];
+    if (p != w->rank && pid > 0 && !proc_alive(pid))
+      xfail("comm: rank %d (pid %d) is gone while rank %d waits in %s", p, pid, w->rank, what);
+  }
+  if (now - t0 > host_timeout())
+    xfail("comm: rank %d waited more than %.0f s in %s (EXAGS_HOST_TIMEOUT_S)", w->rank, host_timeout(), what);
+}
+
 static void make_key(struct xg_world *w)
 {
   const char *k = getenv("EXAGS_JOB_KEY");
   if (k && *k) { snprintf(w->key, sizeof w->key, "%.48s", k); return; }
   /* every rank of one launch has the same parent (torchrun agent, mpirun,
      a test harness): key on that parent's pid and start time */
-  unsigned long long start = 0;
-  char path[64], line[1024];
-  snprintf(path, sizeof path, "/proc/%d/stat", (int)getppid());
-  FILE *f = fopen(path, "r");
-  if (f) {
-    if (fgets(line, sizeof line, f)) {
-      char *p = strrchr(line, ')');
-      int field = 2;
-      while (p && *p && field < 22) { if (*p == ' ') ++field; ++p; }
-      if (p) start = strtoull(p, 0, 10);
-    }
-    fclose(f);
-  }
+  const unsigned long long start = proc_start_time((int)getppid());
   const char *port = getenv("MASTER_PORT");
   /* an elastic launcher restarts its workers under the same agent: the restart
      count keeps a new attempt off the segment a failed one may have left */
@@ -145,37 +195,53 @@ static void rendezvous_attach(struct xg_world *w)
     if (ftruncate(fd, (off_t)sizeof(struct xw_ctl)) != 0)
       xfail("comm: cannot size rendezvous segment: %s", strerror(errno));
   } else {
-    unsigned spins = 0; double waited = 0;
+    /* A segment of this name may be the leftover of a killed run with the same
+       key (only atexit unlinks): it is this launch's only if its owner -- the
+       process that initialised it -- is alive and is the process it says it
+       is.  Anything else is skipped until rank 0 has replaced it.            */
+    unsigned spins = 0; double t0, now; exags_comm_time(&t0);
     for (;;) {
       fd = shm_open(name, O_RDWR, 0600);
       if (fd >= 0) {
         struct stat st;
-        if (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(struct xw_ctl)) break;
+        if (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(struct xw_ctl)) {
+          struct xw_ctl *c = (struct xw_ctl *)mmap(0, sizeof(struct xw_ctl), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+          if (c != MAP_FAILED) {
+            const int owner = c->pid[0];
+            if (atomic_load(&c->magic) == XW_MAGIC && owner > 0 && c->owner_start &&
+                proc_start_time(owner) == c->owner_start) { w->ctl = c; close(fd); break; }
+            munmap(c, sizeof(struct xw_ctl));
+          }
+        }
         close(fd); fd = -1;
       }
       relax(&spins);
-      if (spins >= 2000) waited += 50e-6;
-      if (waited > 120.0) xfail("comm: rank %d timed out waiting for rank 0's rendezvous segment %s", w->rank, name);
+      exags_comm_time(&now);
+      if (now - t0 > 120.0) xfail("comm: rank %d timed out waiting for rank 0's rendezvous segment %s", w->rank, name);
     }
   }
-  w->ctl = (struct xw_ctl *)mmap(0, sizeof(struct xw_ctl), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-  close(fd);
-  if (w->ctl == MAP_FAILED) xfail("comm: mmap of rendezvous segment failed: %s", strerror(errno));
   if (w->rank == 0) {
+    w->ctl = (struct xw_ctl *)mmap(0, sizeof(struct xw_ctl), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (w->ctl == MAP_FAILED) xfail("comm: mmap of rendezvous segment failed: %s", strerror(errno));
     w->ctl->np = (unsigned)w->np;
+    w->ctl->pid[0] = (int)getpid();
+    w->ctl->owner_start = proc_start_time((int)getpid());
     atomic_store(&w->ctl->attached, 1u);
     atomic_store(&w->ctl->bar_count, 0u);
     atomic_store(&w->ctl->bar_sense, 0u);
     atomic_store(&w->ctl->magic, XW_MAGIC);
   } else {
-    unsigned spins = 0;
-    while (atomic_load(&w->ctl->magic) != XW_MAGIC) relax(&spins);
     if (w->ctl->np != (unsigned)w->np)
       xfail("comm: rendezvous segment is for %u ranks, this job has %d", w->ctl->np, w->np);
+    w->ctl->pid[w->rank] = (int)getpid();
     atomic_fetch_add(&w->ctl->attached, 1u);
   }
-  unsigned spins = 0;
-  while (atomic_load(&w->ctl->attached) < (unsigned)w->np) relax(&spins);
+  unsigned spins = 0; double t0; exags_comm_time(&t0);
+  while (atomic_load(&w->ctl->attached) < (unsigned)w->np) {
+    relax(&spins);
+    if ((spins & 0x3fffu) == 0) wait_check(w, t0, "comm_init (not every rank has attached)");
+  }
   w->sense = 0;
 }
 
@@ -187,8 +253,14 @@ void xg_host_barrier(struct xg_world *w)
     atomic_store(&w->ctl->bar_count, 0u);
     atomic_store(&w->ctl->bar_sense, mine);
   } else {
-    unsigned spins = 0;
-    while (atomic_load(&w->ctl->bar_sense) != mine) relax(&spins);
+    unsigned spins = 0; double t0 = 0;
+    while (atomic_load(&w->ctl->bar_sense) != mine) {
+      relax(&spins);
+      if ((spins & 0x3fffu) == 0) {               /* about once a second once the wait sleeps */
+        if (t0 == 0) exags_comm_time(&t0);
+        wait_check(w, t0, "a host barrier");
+      }
+    }
   }
 }
 

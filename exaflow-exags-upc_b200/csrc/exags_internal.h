@@ -204,6 +204,8 @@ void  *xcu_event_create(void);
 void  *xcu_event_create_timed(void);
 void   xcu_event_destroy(void *ev);
 float  xcu_event_ms(void *a, void *b);
+void   xcu_event_sync(void *ev);
+int    xcu_event_done(void *ev);                    /* 1 when the event has completed */
 void   xcu_event_record(void *ev, void *stream);
 void   xcu_stream_wait_event(void *stream, void *ev);
 void   xcu_device_sync(void);
@@ -240,6 +242,7 @@ struct xcu_sell {
   const unsigned char *mask;
   const u32 *idx;
   const unsigned char *fmask;   /* NULL: no flagged members */
+  u32 occ;                      /* resident CTAs per SM the plain kernels are compiled for: 0 = default */
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose);
@@ -346,6 +349,10 @@ struct xcu_dsell {              /* struct xg_sell in HBM                       *
 void xcu_setup_topo(const void *id, int idbytes, size_t n, struct xcu_topo *t);
 void xcu_setup_topo_free(struct xcu_topo *t);
 void xcu_setup_topo_to_host(const struct xcu_topo *dt, struct xg_topo *ht);
+struct xg_cand; struct xg_world;
+/* np > 1: candidate labels chosen on the device (collective over the ranks of w) */
+void xcu_setup_candidates(const struct xcu_topo *t, struct xg_world *w, struct xg_cand *out);
+void xcu_setup_bgrp(const struct xcu_topo *t, const u32 *bprim, u32 nb, u32 *bgrp);
 /* hall: every group with >= 2 members; fp: all flagged primaries; fs: flagged
    primaries that head no multi-member group; sectors: distinct 32-byte sectors
    of a double field that hold a member of hall                               */

@@ -946,8 +946,14 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
     xcu_field f1 = *f;
     f1.vn = 1; f1.tuple = 1;
     mode = XM_PLAIN;
+    /* 4-byte elements: 8 resident CTAs per SM (32 registers, no spills) */
 #define X(T, OP, MODE)                                                        \
-  k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0)
+  do {                                                                        \
+    if (m->occ ? m->occ >= 8 : sizeof(T) == 4)                                \
+      k_fused_sell<T, OP, XM_PLAIN, 1, 8><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0); \
+    else                                                                      \
+      k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0); \
+  } while (0)
     FOR_DOM(XM_PLAIN, X)
 #undef X
   } else if (mode == XM_VEC && f->vn == 3 && f->tuple == 3 && f->k0 == 0 &&
@@ -1268,6 +1274,14 @@ float xcu_event_ms(void *a, void *b)
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b));
   return ms;
+}
+void xcu_event_sync(void *ev) { CU(cudaEventSynchronize((cudaEvent_t)ev)); }
+int xcu_event_done(void *ev)
+{
+  cudaError_t e = cudaEventQuery((cudaEvent_t)ev);
+  if (e == cudaSuccess) return 1;
+  if (e != cudaErrorNotReady) CU(e);
+  return 0;
 }
 void xcu_event_record(void *ev, void *st) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
 void xcu_stream_wait_event(void *st, void *ev) { CU(cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)ev, 0)); }

@@ -23,6 +23,7 @@
 #include "sell_window.h"
 
 struct dev_csr { struct xcu_csr c; u32 *off, *idx, *nunf; };
+#define XG_RING 3                     /* slots of each pinned bounce ring (pageable host arrays) */
 
 
 struct gs_data {
@@ -55,6 +56,10 @@ struct gs_data {
   u32 *pipe_run;                      /* [chunks] windows runnable once chunks 0..k are on the device */
   u32 *pipe_out_wave;                 /* [chunks] wave after which chunk j is final */
   void **pipe_ev;                     /* [2*chunks] events */
+  /* pageable caller arrays on the pipelined path: pinned bounce rings */
+  char *ring_in[XG_RING], *ring_out[XG_RING];
+  size_t ring_bytes;
+  void *ring_ev_in[XG_RING], *ring_ev_out[XG_RING];
   u32 nfs;                    /* flagged primaries heading no group, not boundary: one-member groups
                                  of the interior map (their reduction is the identity gs_init writes) */
   struct xcu_bnd d_bnd;       /* boundary primaries */
@@ -74,6 +79,14 @@ struct gs_data {
 };
 
 /* ------------------------------------------------------------------ */
+/* EXAGS_SELL_OCC=6|8 (read at gs_setup, for A/B runs): resident CTAs per SM of
+   the plain sliced kernel; unset: 8 for 4-byte elements, 6 for 8-byte ones    */
+static u32 sell_occ(void)
+{
+  const char *e = getenv("EXAGS_SELL_OCC");
+  return e ? (u32)atoi(e) : 0u;
+}
+
 static void *upload(const void *src, size_t bytes)
 {
   void *d = xcu_malloc(bytes);
@@ -501,8 +514,47 @@ static void pipe_plan(struct gs_data *g)
   g->pipe_chunks = C;
 }
 
+/* memcpy spread over this rank's share of the host cores */
+static void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+  const int nthr = xg_setup_threads();
+  const size_t piece = (size_t)1 << 20;
+  if (nthr <= 1 || bytes < 4 * piece) { memcpy(dst, src, bytes); return; }
+  const long np = (long)((bytes + piece - 1) / piece);
+  (void)nthr;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthr)
+#endif
+  for (long i = 0; i < np; ++i) {
+    const size_t o = (size_t)i * piece, len = bytes - o < piece ? bytes - o : piece;
+    memcpy((char *)dst + o, (const char *)src + o, len);
+  }
+}
+
+/* chunks on their way out of the pinned ring into the caller's pageable array, oldest first */
+struct ring_out_q { unsigned head, count, chunk[XG_RING]; };
+
+static void ring_ensure(struct gs_data *g, size_t bytes)
+{
+  if (g->ring_bytes >= bytes) return;
+  xcu_device_sync();
+  for (int k = 0; k < XG_RING; ++k) {
+    xcu_host_free(g->ring_in[k]); xcu_host_free(g->ring_out[k]);
+    g->ring_in[k] = (char *)xcu_host_alloc(bytes); g->ring_out[k] = (char *)xcu_host_alloc(bytes);
+    if (!g->ring_ev_in[k]) { g->ring_ev_in[k] = xcu_event_create(); g->ring_ev_out[k] = xcu_event_create(); }
+  }
+  g->ring_bytes = bytes;
+}
+
+/* pageable: the caller's arrays are ordinary host memory (the reference's
+   calling convention, src/gs.upc:1187-1191).  A copy engine cannot read them,
+   and the driver's own staging of a cudaMemcpyAsync on pageable memory is
+   serial and slow (115 ms per call at M7 against 18 ms from pinned memory,
+   profiles/r2_bench_N1_b_pageable.json).  Chunks therefore pass through two
+   small rings of pinned buffers, filled and emptied by this rank's host cores
+   while the copy engines and the kernels work on the neighbouring chunks.   */
 static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode, unsigned vn,
-                                  int xd, int xop, int transpose)
+                                  int xd, int xop, int transpose, int pageable)
 {
   struct xg_world *w = g->w;
   const unsigned C = g->pipe_chunks;
@@ -510,6 +562,7 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
   const unsigned parts = mode == XM_MANY ? vn : 1;
   const size_t tuple = mode == XM_VEC ? vn : 1;           /* elements per index */
   const size_t each = n * esz * tuple;
+  const size_t cbytes = per * esz * tuple;                /* one chunk of one part */
   char *stage = (char *)xg_world_scratch(w, 2, each * parts);
   void *s_in = xg_world_stream(w, 2), *s_run = xg_world_stream(w, 0), *s_out = xg_world_stream(w, 3);
   void *scomm = xg_world_stream(w, 1);
@@ -518,16 +571,50 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
   void *dptr[XG_MAXV];
   if (mode == XM_MANY) { if (vn > XG_MAXV) xfail("gs: internal: pipelined path with %u arrays", vn); for (unsigned k = 0; k < vn; ++k) dptr[k] = f.p[k] = stage + each * k; }
   else dptr[0] = f.p[0] = stage;
+  if (pageable) ring_ensure(g, cbytes * parts);
+  struct ring_out_q q; memset(&q, 0, sizeof q);
+  unsigned nout = 0;
   /* np > 1: the boundary groups run once the whole field is up (their members
      sit in the first and last layers of a slab); the chunks they touch go
      back after the unpack, every other chunk as soon as its windows are done */
   struct bnd_ctx bc;
   bnd_prepare(g, &bc, vn, xd, xop, transpose);
   u32 done = 0;
+#define CHUNK_BYTES(j) ((((size_t)(j) * per + per < n ? (size_t)(j) * per + per : n) - (size_t)(j) * per) * esz * tuple)
+#define RING_DRAIN_ONE() do {                                                              \
+    const unsigned j_ = q.chunk[q.head], sl_ = (nout - q.count) % XG_RING;                 \
+    xcu_event_sync(g->ring_ev_out[sl_]);                                                   \
+    for (unsigned p = 0; p < parts; ++p)                                                   \
+      par_memcpy((char *)ptrs[p] + (size_t)j_ * per * esz * tuple, g->ring_out[sl_] + cbytes * p, CHUNK_BYTES(j_)); \
+    q.head = (q.head + 1) % XG_RING; --q.count;                                            \
+  } while (0)
+#define CHUNK_OUT(j) do {                                                                  \
+    const size_t olo_ = (size_t)(j) * per, ob_ = CHUNK_BYTES(j);                           \
+    if (!pageable) {                                                                       \
+      for (unsigned p = 0; p < parts; ++p)                                                 \
+        xcu_d2h((char *)ptrs[p] + olo_ * esz * tuple, stage + each * p + olo_ * esz * tuple, ob_, s_out); \
+    } else {                                                                               \
+      if (q.count == XG_RING) RING_DRAIN_ONE();                                            \
+      const unsigned sl_ = nout % XG_RING;                                                 \
+      for (unsigned p = 0; p < parts; ++p)                                                 \
+        xcu_d2h(g->ring_out[sl_] + cbytes * p, stage + each * p + olo_ * esz * tuple, ob_, s_out); \
+      xcu_event_record(g->ring_ev_out[sl_], s_out);                                        \
+      q.chunk[(q.head + q.count) % XG_RING] = (unsigned)(j); ++q.count; ++nout;            \
+    }                                                                                      \
+  } while (0)
   for (unsigned k = 0; k < C; ++k) {
     size_t lo = (size_t)k * per, hi = lo + per < n ? lo + per : n;
-    for (unsigned p = 0; p < parts; ++p)
-      xcu_h2d(stage + each * p + lo * esz * tuple, (const char *)ptrs[p] + lo * esz * tuple, (hi - lo) * esz * tuple, s_in);
+    if (pageable) {
+      const unsigned sl = k % XG_RING;
+      if (k >= XG_RING) xcu_event_sync(g->ring_ev_in[sl]);       /* its previous upload has left the slot */
+      for (unsigned p = 0; p < parts; ++p)
+        par_memcpy(g->ring_in[sl] + cbytes * p, (const char *)ptrs[p] + lo * esz * tuple, (hi - lo) * esz * tuple);
+      for (unsigned p = 0; p < parts; ++p)
+        xcu_h2d(stage + each * p + lo * esz * tuple, g->ring_in[sl] + cbytes * p, (hi - lo) * esz * tuple, s_in);
+      xcu_event_record(g->ring_ev_in[sl], s_in);
+    } else
+      for (unsigned p = 0; p < parts; ++p)
+        xcu_h2d(stage + each * p + lo * esz * tuple, (const char *)ptrs[p] + lo * esz * tuple, (hi - lo) * esz * tuple, s_in);
     xcu_event_record(g->pipe_ev[k], s_in);
     xcu_stream_wait_event(s_run, g->pipe_ev[k]);
     if (g->pipe_run[k] > done) {
@@ -547,22 +634,24 @@ static void gs_run_host_pipelined(struct gs_data *g, void *const *ptrs, int mode
     }
     for (unsigned j = 0; j < C; ++j) {
       if (g->pipe_out_wave[j] != k || (bc.active && g->pipe_bnd[j])) continue;
-      size_t olo = (size_t)j * per, ohi = olo + per < n ? olo + per : n;
       xcu_stream_wait_event(s_out, g->pipe_ev[C + k]);
-      for (unsigned p = 0; p < parts; ++p)
-        xcu_d2h((char *)ptrs[p] + olo * esz * tuple, stage + each * p + olo * esz * tuple, (ohi - olo) * esz * tuple, s_out);
+      CHUNK_OUT(j);
     }
+    /* hand finished chunks back while the next ones are in flight */
+    while (pageable && q.count && xcu_event_done(g->ring_ev_out[(nout - q.count) % XG_RING])) RING_DRAIN_ONE();
   }
   if (bc.active) {
     xcu_stream_wait_event(s_out, xg_world_event(w, 1));
     xcu_stream_wait_event(s_out, g->pipe_ev[2 * C - 1]);
     for (unsigned j = 0; j < C; ++j) {
       if (!g->pipe_bnd[j]) continue;
-      size_t olo = (size_t)j * per, ohi = olo + per < n ? olo + per : n;
-      for (unsigned p = 0; p < parts; ++p)
-        xcu_d2h((char *)ptrs[p] + olo * esz * tuple, stage + each * p + olo * esz * tuple, (ohi - olo) * esz * tuple, s_out);
+      CHUNK_OUT(j);
     }
   }
+  while (q.count) RING_DRAIN_ONE();
+#undef CHUNK_OUT
+#undef RING_DRAIN_ONE
+#undef CHUNK_BYTES
   xcu_stream_sync(s_out);
   xcu_stream_sync(s_run);
   if (bc.active) xcu_stream_sync(scomm);
@@ -656,7 +745,9 @@ static void gs_run(void *u, int mode, unsigned vn, int dom, int op, unsigned tra
     const char *pp = getenv("EXAGS_HOST_PIPELINE");
     if (!(pp && atoi(pp) == 0)) pipe_plan(g);
     if (g->pipe_chunks) {
-      gs_run_host_pipelined(g, ptrs, mode, vn, xd, op, (int)transpose);
+      int pageable = 0;
+      for (unsigned k = 0; k < (mode == XM_MANY ? vn : 1u); ++k) pageable |= xcu_ptr_kind(ptrs[k]) == 0;
+      gs_run_host_pipelined(g, ptrs, mode, vn, xd, op, (int)transpose, pageable);
       if (ptrs != ptrs_few) free(ptrs);
       return;
     }
@@ -860,6 +951,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
+    g->d_sell.occ = sell_occ();
       g->d_sell.nblock = sell.nblock;
     g->d_sell_mem[0] = upload(sell.mask, (size_t)sell.nblock * 32 + 1);
     g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
@@ -1011,6 +1103,7 @@ static void adopt_interior(struct gs_data *g, const struct xcu_dmap *in, const s
 {
   struct xcu_dsell ds;
   xcu_setup_sell(in, &ds);
+  g->d_sell.occ = sell_occ();
   g->d_sell.nblock = ds.nblock;
   g->d_sell.mask = ds.mask; g->d_sell.idx = ds.idx; g->d_sell.fmask = ds.fmask;
   g->d_sell_mem[0] = ds.mask; g->d_sell_mem[1] = ds.idx; g->d_sell_mem[2] = ds.fmask;
@@ -1192,24 +1285,34 @@ static struct gs_data *setup_core(const void *id_in, int idbytes, u32 n, const c
   }
   const int dev_split = np > 1 && setup_on_device(g) && !(lay && strcmp(lay, "csr") == 0);
   if (dev_split) {
-    /* topology on the device; it also comes back for the shared-label
-       discovery and the exchange plan, which are host code */
+    /* topology on the device, and it stays there: the labels another rank may
+       hold are picked in HBM, only those candidates come to the host for the
+       rendezvous on id % np (shared_ids, src/gs.upc:190-244) and the exchange
+       plan, and the plan's boundary primaries are matched to their groups on
+       the device again */
     struct xcu_topo dt;
+    struct xg_cand cand;
+    memset(&topo, 0, sizeof topo);
     xcu_setup_begin();
     xcu_setup_topo(id, idbytes, n, &dt);
-    xcu_setup_topo_to_host(&dt, &topo);
     TICK();
-    xg_shared_discover(&sh, &topo, w);
+    xcu_setup_candidates(&dt, w, &cand);
+    xg_shared_pair(&sh, &cand, w);
+    xg_cand_free(&cand);
     TICK();
     g->handle_bytes = sizeof *g;
-    xg_plan_build(&g->plan, &sh, &topo);
+    xg_plan_build(&g->plan, &sh, 0);
+    xcu_setup_bgrp(&dt, g->plan.bprim, g->plan.nb, g->plan.bgrp);
+    for (u32 b = 0; b < g->plan.nb; ++b)
+      if (g->plan.bgrp[b] == XG_NONE)
+        xfail("gs_setup: shared label's primary index %u is not a local primary", g->plan.bprim[b]);
     TICK();
     split_groups_device(g, &dt);
     xcu_setup_topo_free(&dt);
     xcu_setup_end();
     TICK();
     if (prof)
-      printf("gs_setup profile (rank 0, n=%u, device): label sort+groups+fetch %.3f s, shared discovery %.3f s, "
+      printf("gs_setup profile (rank 0, n=%u, device): label sort+groups %.3f s, shared discovery %.3f s, "
              "exchange plan %.3f s, split + sliced layouts %.3f s\n", n,
              tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
   } else {
@@ -1308,6 +1411,10 @@ void exags_gs_free(struct gs_data *g)
     xg_mbox_free(g->w, &g->mbox);
     if (g->dev_built) { xcu_dmap_free(&g->d_hall); xcu_free(g->d_hfp); }
     for (unsigned k = 0; g->pipe_ev && k < 2 * g->pipe_chunks; ++k) xcu_event_destroy(g->pipe_ev[k]);
+    for (int k = 0; k < XG_RING; ++k) {
+      xcu_host_free(g->ring_in[k]); xcu_host_free(g->ring_out[k]);
+      xcu_event_destroy(g->ring_ev_in[k]); xcu_event_destroy(g->ring_ev_out[k]);
+    }
   }
   xg_hmap_free(&g->hall);
   free(g->hfp); free(g->win_min); free(g->win_max); free(g->pipe_run); free(g->pipe_out_wave); free(g->pipe_ev);

@@ -45,6 +45,11 @@ struct xg_plan {
   u32  nsym, *sym_rank;
 };
 
+/* labels of this rank that some other rank may hold too: |label| and the
+   primary's local index (complemented when the primary is flagged)          */
+struct xg_cand { size_t n; u64 *id; u32 *src_if; };
+void xg_cand_free(struct xg_cand *c);
+void xg_shared_pair(struct xg_shared *out, const struct xg_cand *c, struct xg_world *w);
 void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w);
 void xg_shared_free(struct xg_shared *s);
 void xg_unique_flags(unsigned char *newflag, size_t n, const struct xg_topo *t,

@@ -33,16 +33,16 @@ void xg_shared_free(struct xg_shared *s)
   memset(s, 0, sizeof *s);
 }
 
-void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w)
+void xg_cand_free(struct xg_cand *c) { free(c->id); free(c->src_if); memset(c, 0, sizeof *c); }
+
+/* Candidate labels of this rank, chosen on the host from the host copy of the
+   topology (EXAGS_SETUP=host, gs_unique, setup with unique=1).  The device
+   passes of setup_cuda.cu (xcu_setup_candidates) apply the same two filters
+   in HBM and bring back only the candidates.                               */
+static void shared_candidates_host(struct xg_cand *out, const struct xg_topo *t, struct xg_world *w)
 {
   const int np = xg_world_np(w), me = xg_world_rank(w);
   memset(out, 0, sizeof *out);
-  if (np == 1) return;
-  const char *prof_env = getenv("EXAGS_SETUP_PROFILE");
-  const int prof = prof_env && atoi(prof_env) >= 2 && me == 0;
-  double tp[8]; int ntp = 0;
-#define TICK() do { if (prof) exags_comm_time(&tp[ntp++]); } while (0)
-  TICK();
 
   /* Which of my labels can another rank hold at all?  The reference ships every
      local label to its work rank (src/gs.upc:118-131); on a spectral-element
@@ -139,23 +139,56 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
 #undef LABEL_BIT
     free(others);
   }
-  TICK();
-
-  /* one row per candidate label, grouped by work rank id % np (src/gs.upc:118-131) */
-  size_t *cnt = xnew0(size_t, np), *pos = xnew(size_t, np);
-  size_t nsend = 0;
-  for (size_t g = 0; g < t->ngrp; ++g) if (cand[g]) { ++cnt[t->id[g] % (u64)np]; ++nsend; }
-  { size_t run = 0; for (int p = 0; p < np; ++p) { pos[p] = run; run += cnt[p]; } }
-  struct uq_row *send = xnew(struct uq_row, nsend ? nsend : 1);
+  size_t nc = 0;
+  for (size_t g = 0; g < t->ngrp; ++g) nc += cand[g];
+  out->n = nc;
+  out->id = xnew(u64, nc ? nc : 1); out->src_if = xnew(u32, nc ? nc : 1);
+  nc = 0;
   for (size_t g = 0; g < t->ngrp; ++g) {
     if (!cand[g]) continue;
-    u32 a = t->gstart[g];
-    struct uq_row *r = send + pos[t->id[g] % (u64)np]++;
-    r->id = t->id[g];
-    r->src_if = t->flag[a] ? ~t->idx[a] : t->idx[a];
-    r->pad = 0;
+    const u32 a = t->gstart[g];
+    out->id[nc] = t->id[g];
+    out->src_if[nc] = t->flag[a] ? ~t->idx[a] : t->idx[a];
+    ++nc;
   }
   free(cand);
+}
+
+void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct xg_world *w)
+{
+  memset(out, 0, sizeof *out);
+  if (xg_world_np(w) == 1) return;
+  struct xg_cand c;
+  shared_candidates_host(&c, t, w);
+  xg_shared_pair(out, &c, w);
+  xg_cand_free(&c);
+}
+
+/* The rendezvous of shared_ids (src/gs.upc:190-244) on the candidate labels:
+   one row per candidate goes to its work rank id % np, which pairs the ranks
+   holding the same label and sends the pair rows back.                      */
+void xg_shared_pair(struct xg_shared *out, const struct xg_cand *c, struct xg_world *w)
+{
+  const int np = xg_world_np(w), me = xg_world_rank(w);
+  memset(out, 0, sizeof *out);
+  if (np == 1) return;
+  const char *prof_env = getenv("EXAGS_SETUP_PROFILE");
+  const int prof = prof_env && atoi(prof_env) >= 2 && me == 0;
+  double tp[8]; int ntp = 0;
+#define TICK() do { if (prof) exags_comm_time(&tp[ntp++]); } while (0)
+  TICK();
+  /* one row per candidate label, grouped by work rank id % np (src/gs.upc:118-131) */
+  size_t *cnt = xnew0(size_t, np), *pos = xnew(size_t, np);
+  const size_t nsend = c->n;
+  for (size_t k = 0; k < nsend; ++k) ++cnt[c->id[k] % (u64)np];
+  { size_t run = 0; for (int p = 0; p < np; ++p) { pos[p] = run; run += cnt[p]; } }
+  struct uq_row *send = xnew(struct uq_row, nsend ? nsend : 1);
+  for (size_t k = 0; k < nsend; ++k) {
+    struct uq_row *r = send + pos[c->id[k] % (u64)np]++;
+    r->id = c->id[k];
+    r->src_if = c->src_if[k];
+    r->pad = 0;
+  }
   TICK();
   size_t *rcnt = xnew(size_t, np), nrecv = 0;
   struct uq_row *un = (struct uq_row *)xg_host_alltoallv(w, send, sizeof *send, cnt, rcnt, &nrecv);
@@ -249,8 +282,8 @@ void xg_shared_discover(struct xg_shared *out, const struct xg_topo *t, struct x
   free(back);
   TICK();
   if (prof)
-    printf("shared discovery (rank 0): presence bitmaps %.3f s, candidate rows %.3f s, to work ranks %.3f s, "
-           "pairing + return %.3f s\n", tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3]);
+    printf("shared discovery (rank 0): %lu candidate rows %.3f s, to work ranks %.3f s, "
+           "pairing + return %.3f s\n", (unsigned long)nsend, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2]);
 #undef TICK
 }
 
@@ -364,8 +397,9 @@ void xg_plan_build(struct xg_plan *pl, struct xg_shared *sh, const struct xg_top
       bof[perm[k]] = b;
     }
   }
-  /* topology group of each boundary primary (both lists ascend by primary) */
-  {
+  /* topology group of each boundary primary (both lists ascend by primary);
+     with t == NULL the caller fills bgrp from the device topology */
+  if (t) {
     size_t g = 0;
     for (u32 b = 0; b < nb; ++b) {
       while (g < t->ngrp && t->idx[t->gstart[g]] < pl->bprim[b]) ++g;

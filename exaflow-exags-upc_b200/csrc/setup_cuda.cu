@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "setup_pipeline.h"
+#include "gs_plan.h"
 
 #define CU(call)                                                              \
   do {                                                                        \
@@ -272,6 +273,89 @@ void xcu_setup_split(const struct xcu_topo *t, const u32 *bgrp_host, u32 nb, str
   check(xgsetup::split_maps(be, t, bgrp, nb, hall, in, bnd, bnd2, fp, nfp, fs, nfs, sectors), "interior/boundary split");
   be.release(bgrp);
   CU(cudaStreamSynchronize(be.st));
+}
+
+/* np > 1: the labels of this rank that another rank may hold too, chosen in
+   HBM (setup_pipeline.h) with the two filters of remote.c -- the ranks trade
+   an 8 KB range-occupancy bitmap and a hashed presence bitmap through the host
+   rendezvous -- so that only the candidates (the interface labels of a
+   partitioned mesh, well under 1 % of the topology) come back to the host.  */
+void xcu_setup_candidates(const struct xcu_topo *t, struct xg_world *w, struct xg_cand *out)
+{
+  Scope sc; CudaBackend &be = sc.be;
+  const int np = xg_world_np(w), me = xg_world_rank(w);
+  memset(out, 0, sizeof *out);
+  const size_t ngrp = t->ngrp;
+  u64 lmax = ngrp ? be.max_u64(t->id, ngrp) : 0, gmax = 0;
+  u64 *all = xnew(u64, (size_t)np > 2 ? (size_t)np : 2);
+  xg_host_allgather(w, &lmax, sizeof lmax, all);
+  for (int p = 0; p < np; ++p) if (all[p] > gmax) gmax = all[p];
+  unsigned shift = 0;
+  while ((gmax >> shift) >= (u64)xgsetup::CAND_BINS) ++shift;
+
+  /* stage 1: coarse bins */
+  const size_t bw = xgsetup::CAND_BINS / 64;
+  u32 *bins = be.alloc<u32>(2 * bw);
+  be.zero(bins, 2 * bw * sizeof(u32));
+  xgsetup::cand_bins(be, t, shift, bins);
+  u64 *hb = xnew(u64, bw), *allb = xnew(u64, (size_t)np * bw);
+  CU(cudaMemcpyAsync(hb, bins, bw * sizeof(u64), cudaMemcpyDeviceToHost, be.st));
+  CU(cudaStreamSynchronize(be.st));
+  xg_host_allgather(w, hb, bw * sizeof(u64), allb);
+  memset(hb, 0, bw * sizeof(u64));
+  for (int p = 0; p < np; ++p)
+    if (p != me) for (size_t k = 0; k < bw; ++k) hb[k] |= allb[(size_t)p * bw + k];
+  CU(cudaMemcpyAsync(bins, hb, bw * sizeof(u64), cudaMemcpyHostToDevice, be.st));
+  u32 *c32 = be.alloc<u32>(ngrp + 1);
+  xgsetup::cand_from_bins(be, t, shift, bins, c32);
+  u64 npass = ngrp ? be.sum_u32(c32, ngrp) : 0, maxn = 1;
+  free(hb); free(allb);
+  be.release(bins);
+
+  /* stage 2: hashed presence bitmap of what passed */
+  xg_host_allgather(w, &npass, sizeof npass, all);
+  for (int p = 0; p < np; ++p) if (all[p] > maxn) maxn = all[p];
+  free(all);
+  unsigned bits = 20;
+  while (bits < 34 && ((u64)1 << bits) < 16 * maxn) ++bits;          /* <= 1/16 full: ~6 % false positives */
+  const size_t words = (size_t)1 << (bits - 6);
+  u32 *bm = be.alloc<u32>(2 * words);
+  be.zero(bm, 2 * words * sizeof(u32));
+  xgsetup::cand_presence(be, t, c32, bits, bm);
+  u64 *mine = xg_host_bitmap_new(w, words), *others = xnew(u64, words);
+  CU(cudaMemcpyAsync(mine, bm, words * sizeof(u64), cudaMemcpyDeviceToHost, be.st));
+  CU(cudaStreamSynchronize(be.st));
+  xg_host_bitmap_or_others(w, mine, words, others);                   /* releases mine */
+  CU(cudaMemcpyAsync(bm, others, words * sizeof(u64), cudaMemcpyHostToDevice, be.st));
+  xgsetup::cand_refine(be, t, c32, bits, bm);
+  CU(cudaStreamSynchronize(be.st));
+  free(others);
+  be.release(bm);
+
+  u64 *d_id = nullptr; u32 *d_sif = nullptr;
+  const u32 cnt = xgsetup::cand_compact(be, t, c32, &d_id, &d_sif);
+  be.release(c32);
+  out->n = cnt;
+  out->id = xnew(u64, cnt ? cnt : 1); out->src_if = xnew(u32, cnt ? cnt : 1);
+  if (cnt) {
+    CU(cudaMemcpyAsync(out->id, d_id, (size_t)cnt * sizeof(u64), cudaMemcpyDeviceToHost, be.st));
+    CU(cudaMemcpyAsync(out->src_if, d_sif, (size_t)cnt * sizeof(u32), cudaMemcpyDeviceToHost, be.st));
+  }
+  CU(cudaStreamSynchronize(be.st));
+  be.release(d_id); be.release(d_sif);
+}
+
+/* topology group of each boundary primary the exchange plan named (host arrays) */
+void xcu_setup_bgrp(const struct xcu_topo *t, const u32 *bprim, u32 nb, u32 *bgrp)
+{
+  if (!nb) return;
+  Scope sc; CudaBackend &be = sc.be;
+  u32 *d_p = be.alloc<u32>(nb), *d_g = be.alloc<u32>(nb);
+  CU(cudaMemcpyAsync(d_p, bprim, (size_t)nb * sizeof(u32), cudaMemcpyHostToDevice, be.st));
+  xgsetup::groups_of_primaries(be, t, d_p, nb, d_g);
+  CU(cudaMemcpyAsync(bgrp, d_g, (size_t)nb * sizeof(u32), cudaMemcpyDeviceToHost, be.st));
+  CU(cudaStreamSynchronize(be.st));
+  be.release(d_p); be.release(d_g);
 }
 
 void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)

@@ -331,6 +331,107 @@ int split_maps(B &be, const xcu_topo *t, const u32 *bgrp, u32 nb, xcu_dmap *hall
   return OK;
 }
 
+// ---------------------------------------------------------------------------
+// which labels can another rank hold?  (the filters in front of unique_ids /
+// shared_ids, src/gs.upc:117-131,190-244; host form in remote.c)
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define XG_ATOMIC_OR32(p, v) atomicOr((p), (v))
+#else
+#define XG_ATOMIC_OR32(p, v) (*(p) |= (v))
+#endif
+enum { CAND_BINS = 65536 };          // coarse label-range bins (one occupancy bit each)
+
+// bins: CAND_BINS / 32 zeroed words; bit b is set when a label with (id >> shift) == b is present.
+// The words are little-endian halves of the host's 64-bit bitmap words.
+template <class B>
+void cand_bins(B &be, const xcu_topo *t, unsigned shift, u32 *bins)
+{
+  const u64 *id = t->id;
+  be.for_each(t->ngrp, [=] XG_DEV(size_t g) {
+    const u64 b = id[g] >> shift;
+    const u32 m = 1u << (b & 31u);
+    if (!(bins[b >> 5] & m)) XG_ATOMIC_OR32(&bins[b >> 5], m);      // few distinct words: test before the atomic
+  });
+}
+
+// c32[g] = 1 when label g lies in a bin some OTHER rank occupies (others = OR of their bins)
+template <class B>
+void cand_from_bins(B &be, const xcu_topo *t, unsigned shift, const u32 *others, u32 *c32)
+{
+  const u64 *id = t->id;
+  const size_t ngrp = t->ngrp;
+  be.for_each(ngrp + 1, [=] XG_DEV(size_t g) {
+    if (g == ngrp) { c32[g] = 0; return; }
+    const u64 b = id[g] >> shift;
+    c32[g] = (others[b >> 5] >> (b & 31u)) & 1u;
+  });
+}
+
+#define XG_LABEL_HASH(id_, bits_) (((id_) * 0x9E3779B97F4A7C15ull) >> (64 - (bits_)))
+
+// presence bitmap (2^bits bits, zeroed) over a hash of the labels that passed the bins
+template <class B>
+void cand_presence(B &be, const xcu_topo *t, const u32 *c32, unsigned bits, u32 *bitmap)
+{
+  const u64 *id = t->id;
+  be.for_each(t->ngrp, [=] XG_DEV(size_t g) {
+    if (!c32[g]) return;
+    const u64 h = XG_LABEL_HASH(id[g], bits);
+    XG_ATOMIC_OR32(&bitmap[h >> 5], 1u << (h & 31u));
+  });
+}
+
+// keep the candidates whose hash bit is set in the OR of the other ranks' presence bitmaps
+template <class B>
+void cand_refine(B &be, const xcu_topo *t, u32 *c32, unsigned bits, const u32 *others)
+{
+  const u64 *id = t->id;
+  be.for_each(t->ngrp, [=] XG_DEV(size_t g) {
+    if (!c32[g]) return;
+    const u64 h = XG_LABEL_HASH(id[g], bits);
+    c32[g] = (others[h >> 5] >> (h & 31u)) & 1u;
+  });
+}
+
+// the candidates in group order: |label| and the primary's index, complemented when the primary is
+// flagged (struct uq_row of remote.c).  c32 (ngrp + 1 entries, last 0) is consumed.
+template <class B>
+u32 cand_compact(B &be, const xcu_topo *t, u32 *c32, u64 **id_out, u32 **sif_out)
+{
+  const size_t ngrp = t->ngrp;
+  be.scan(c32, ngrp + 1);
+  const u32 cnt = be.get(c32 + ngrp);
+  u64 *oid = be.template alloc<u64>((size_t)cnt + 1);
+  u32 *osf = be.template alloc<u32>((size_t)cnt + 1);
+  const u64 *id = t->id;
+  const u32 *gstart = t->gstart, *idx = t->idx;
+  const unsigned char *flag = t->flag;
+  be.for_each(ngrp, [=] XG_DEV(size_t g) {
+    if (c32[g + 1] == c32[g]) return;
+    const u32 o = c32[g], a = gstart[g];
+    oid[o] = id[g];
+    osf[o] = flag[a] ? ~idx[a] : idx[a];
+  });
+  *id_out = oid; *sif_out = osf;
+  return cnt;
+}
+
+// topology group headed by each of the nb primaries bprim (ascending, like the groups' own primaries);
+// XG_NONE where a primary heads no group
+template <class B>
+void groups_of_primaries(B &be, const xcu_topo *t, const u32 *bprim, u32 nb, u32 *bgrp)
+{
+  const size_t ngrp = t->ngrp;
+  const u32 *gstart = t->gstart, *idx = t->idx;
+  be.for_each(nb, [=] XG_DEV(size_t b) {
+    const u32 want = bprim[b];
+    size_t lo = 0, hi = ngrp;                      // first group whose primary is >= want
+    while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (idx[gstart[mid]] < want) lo = mid + 1; else hi = mid; }
+    bgrp[b] = (lo < ngrp && idx[gstart[lo]] == want) ? (u32)lo : XG_NONE;
+  });
+}
+
 template <class B>
 void dmap_release(B &be, xcu_dmap *m)
 {

@@ -77,6 +77,16 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=np_)
     import exags_b200 as X
     import oracle as O
+    if what == "die":
+        # one rank leaves without a word; the others must end in the reference's fail()
+        # ("ERROR (proc ...", exit status 1) instead of spinning in the host barrier
+        X.comm_world()
+        dist.barrier()
+        if rank == np_ - 1:
+            os._exit(7)
+        X.lib().exags_comm_barrier(X.comm_world())
+        X.lib().exags_comm_barrier(X.comm_world())
+        sys.exit(0)
     if gpu:
         ndev = torch.cuda.device_count()
         X.lib().exags_set_device(rank % ndev)

@@ -109,3 +109,15 @@ def test_multirank_setup_fuzz(built, np_, seed):
     for unique in (0, 1):
         codes, outs = run_ranks(np_, [f"fuzz{seed}", "setup", unique])
         assert all(c == 0 for c in codes), "\n".join(outs)
+
+
+def test_dead_rank_ends_the_wait(built):
+    """A rank that dies while the others sit in a host barrier: they fail through
+    the reference's fail() contract (src/fail.upc:19-63) within seconds, not hang."""
+    import time
+    t0 = time.time()
+    codes, outs = run_ranks(3, ["fixture", "die", 0, 1], timeout=120)
+    assert time.time() - t0 < 60
+    assert codes[2] == 7
+    assert codes[0] == 1 and codes[1] == 1, (codes, outs)
+    assert "is gone while rank" in outs[0] and "ERROR (proc" in outs[0]
