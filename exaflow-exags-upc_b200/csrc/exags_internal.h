@@ -242,7 +242,6 @@ struct xcu_sell {
   const unsigned char *mask;
   const u32 *idx;
   const unsigned char *fmask;   /* NULL: no flagged members */
-  u32 occ;                      /* resident CTAs per SM the plain kernels are compiled for: 0 = default */
 };
 void xcu_fused_sell(void *stream, const struct xcu_sell *m, const struct xcu_field *f,
                     int mode, int xdom, int xop, int transpose);

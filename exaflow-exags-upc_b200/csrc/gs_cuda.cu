@@ -252,7 +252,7 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
                                           const unsigned startph, const unsigned flg = 0u,
                                           const int transpose = 0, const T *__restrict__ wgt = nullptr)
 {
-  static_assert(!WGT || (KU == 1 && MODE == XM_PLAIN && !GONLY), "weights: plain fields, full gather-scatter");
+  static_assert(!WGT || !GONLY, "weights: full gather-scatter only");
   const u32 id0[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
   const unsigned start = startph & 0x55u, ph = startph & 0xAAu;
   unsigned mem = 0u;                          // slots that hold a member
@@ -268,7 +268,7 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
     } else in = mem & ~flg;
   }
   if (GONLY) out &= start;
-  // everything below addresses memory in "fetch order": id[], lin, lout
+  // everything below addresses memory in "fetch order": id[], lld, lout
   u32 id[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
@@ -278,7 +278,6 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
   }
   // a phase bit is only ever set on a complete pair: without flags both of its
   // slots contribute and both are written, so the masks need no swapping
-  const unsigned lin = FLG ? swap_pair_bits(in, ph) : in;
   const unsigned lout = (FLG || GONLY) ? swap_pair_bits(out, ph) : out;
   // Every member is loaded, also one whose value does not contribute (a flagged
   // member with transpose == 0): it is written afterwards, and an 8-byte store
@@ -296,10 +295,8 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
     for (int kk = 0; kk < KU; ++kk)
       if (KU == 1 || k0 + kk < f.vn) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j)
           if ((lld >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
-          if (FLG) x[kk][j] = ((lin >> j) & 1u) ? x[kk][j] : ident<T, OP>();
-        }
       }
     T wv[WGT ? 8 : 1];
     if (WGT) {
@@ -321,6 +318,14 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
         const bool sw = (ph >> (j + 1)) & 1u;
         const T p0 = x[kk][j], p1 = x[kk][j + 1];
         x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
+      }
+      // a group whose first member does not contribute (all its members are
+      // flagged, transpose == 0) starts from the identity; the other slots that
+      // do not contribute are skipped by the scan below
+      if (FLG) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2)
+          if (((start & ~in) >> j) & 1u) x[kk][j] = ident<T, OP>();
       }
       // forward: running reduction, restarted where a group begins
 #pragma unroll
@@ -362,13 +367,14 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
   sell_lane<T, OP, MODE, KU, GONLY, FLG, ONE>(f, a, b, start, flg, transpose);
 }
 
-// Weighted form of the two local kernels (exags_gs_weighted: Nek's dssum
-// followed by a multiplication with the inverse multiplicity, fused): plain
-// float/double fields.  8 more bytes per member are read (the weight), against
-// a separate pass over the whole field (read u, read w, write u).
-template <typename T, int OP, int MINB, bool FLG>
+// Weighted form of the two local kernels (exags_gs_weighted[_vec|_many]: Nek's
+// dssum followed by a multiplication with the inverse multiplicity, fused):
+// float/double fields.  One weight per member is read (it applies to every
+// component of a vector field), against a separate pass over the whole field
+// (read u, read w, write u).
+template <typename T, int OP, int MODE, int KU, int MINB, bool FLG, bool ONE>
 __global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
-k_fused_sell_w(xcu_sell m, Fld<T, XM_PLAIN> f, const T *__restrict__ wgt, int transpose)
+k_fused_sell_w(xcu_sell m, Fld<T, MODE> f, const T *__restrict__ wgt, int transpose)
 {
   const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31u;
@@ -376,12 +382,12 @@ k_fused_sell_w(xcu_sell m, Fld<T, XM_PLAIN> f, const T *__restrict__ wgt, int tr
   const uint4 a = __ldg(p), b = __ldg(p + 1);
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const unsigned flg = FLG ? __ldg(m.fmask + (size_t)c * 32u + lane) : 0u;
-  sell_lane<T, OP, XM_PLAIN, 1, false, FLG, false, true>(f, a, b, start, flg, transpose, wgt);
+  sell_lane<T, OP, MODE, KU, false, FLG, ONE, true>(f, a, b, start, flg, transpose, wgt);
 }
 
-template <typename T, int OP>
+template <typename T, int OP, int MODE>
 __global__ void __launch_bounds__(256)
-k_fused_w(xcu_csr m, T *__restrict__ u, const T *__restrict__ wgt, int transpose)
+k_fused_w(xcu_csr m, Fld<T, MODE> f, const T *__restrict__ wgt, int transpose)
 {
   u32 g = blockIdx.x * 256u + threadIdx.x;
   if (g >= m.ng) return;
@@ -389,10 +395,12 @@ k_fused_w(xcu_csr m, T *__restrict__ u, const T *__restrict__ wgt, int transpose
   u32 nall = e - b, nunf = m.nunf ? __ldg(m.nunf + g) : nall, nred, nwr;
   group_counts(nall, nunf, transpose, nred, nwr);
   const u32 *idx = m.idx + b;
-  T v = nred ? u[__ldg(idx)] : ident<T, OP>();
-  for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, u[__ldg(idx + j)]);
-  if (nall == 1u) { u[__ldg(idx)] = v; return; }       // a flagged single: the identity, unweighted
-  for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
+  for (unsigned k = 0; k < f.vn; ++k) {
+    T v = nred ? *f.at(__ldg(idx), k) : ident<T, OP>();
+    for (u32 j = 1; j < nred; ++j) v = apply<T, OP>(v, *f.at(__ldg(idx + j), k));
+    if (nall == 1u) { *f.at(__ldg(idx), k) = v; continue; }    // a flagged single: the identity, unweighted
+    for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); *f.at(i, k) = v * __ldg(wgt + i); }
+  }
 }
 
 // gs_vec with 3-tuples (a velocity field, BASELINE config 3): a tuple is 3
@@ -685,12 +693,12 @@ k_bnd_unpack(xcu_bnd bd, Fld<T, MODE> f, int transpose, const T *__restrict__ re
   }
 }
 
-// weighted form (plain float/double fields): what the unpack writes to a member
+// weighted form (float/double fields): what the unpack writes to a member
 // is the group's result times the member's weight
-template <typename T, int OP>
+template <typename T, int OP, int MODE>
 __global__ void __launch_bounds__(256)
-k_bnd_unpack_w(xcu_bnd bd, T *__restrict__ u, const T *__restrict__ wgt, int transpose,
-               const T *__restrict__ recvbuf, int allreduce, const u32 *depoch, size_t par_bytes)
+k_bnd_unpack_w(xcu_bnd bd, Fld<T, MODE> f, const T *__restrict__ wgt, int transpose,
+               const T *__restrict__ recvbuf, unsigned bufvn, int allreduce, const u32 *depoch, size_t par_bytes)
 {
   if (depoch) recvbuf = reinterpret_cast<const T *>(reinterpret_cast<const char *>(recvbuf) +
                                                     (size_t)(*reinterpret_cast<const volatile u32 *>(depoch) & 1u) * par_bytes);
@@ -700,14 +708,16 @@ k_bnd_unpack_w(xcu_bnd bd, T *__restrict__ u, const T *__restrict__ wgt, int tra
     group_counts(nall, nunf, transpose, nred, nwr);
     const u32 *idx = bd.gidx + gb;
     const int rd = 0 ^ transpose;
-    T v = u[__ldg(idx)];
-    if (allreduce) {
-      if (!transpose || !bd.pflag[b]) v = recvbuf[__ldg(bd.ord + b)];
-    } else {
-      const u32 rb = __ldg(bd.soff[rd] + b), re = __ldg(bd.soff[rd] + b + 1);
-      for (u32 s = rb; s < re; ++s) v = apply<T, OP>(v, recvbuf[__ldg(bd.slot[rd] + s)]);
+    for (unsigned k = 0; k < f.vn; ++k) {
+      T v = *f.at(__ldg(idx), k);
+      if (allreduce) {
+        if (!transpose || !bd.pflag[b]) v = recvbuf[(size_t)__ldg(bd.ord + b) * bufvn + f.k0 + k];
+      } else {
+        const u32 rb = __ldg(bd.soff[rd] + b), re = __ldg(bd.soff[rd] + b + 1);
+        for (u32 s = rb; s < re; ++s) v = apply<T, OP>(v, recvbuf[(size_t)__ldg(bd.slot[rd] + s) * bufvn + f.k0 + k]);
+      }
+      for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); *f.at(i, k) = v * __ldg(wgt + i); }
     }
-    for (u32 j = 0; j < nwr; ++j) { const u32 i = __ldg(idx + j); u[i] = v * __ldg(wgt + i); }
   }
 }
 
@@ -880,7 +890,12 @@ void xcu_fused(void *stream, const xcu_csr *m, const xcu_field *f, int mode, int
   if (!m->ng) return;
   cudaStream_t st = (cudaStream_t)stream;
   if (f->w) {
-#define X(T, OP) k_fused_w<T, OP><<<blocks_for(m->ng), 256, 0, st>>>(*m, (T *)f->p[0], (const T *)f->w, transpose)
+#define X(T, OP)                                                              \
+  do {                                                                        \
+    if (mode == XM_PLAIN) k_fused_w<T, OP, XM_PLAIN><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fld<T, XM_PLAIN>(f), (const T *)f->w, transpose); \
+    else if (mode == XM_VEC) k_fused_w<T, OP, XM_VEC><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fld<T, XM_VEC>(f), (const T *)f->w, transpose); \
+    else k_fused_w<T, OP, XM_MANY><<<blocks_for(m->ng), 256, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, transpose); \
+  } while (0)
     FOR_DOM_W(X)
 #undef X
     LAUNCHED();
@@ -902,17 +917,39 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
   const unsigned grid = m->nblock / XG_SELL_CW;
   const unsigned nthr = 32 * XG_SELL_CW;
   if (f->w) {
-    /* weighted gs: plain float/double fields (checked by the caller) */
-    xcu_field f1 = *f;
-    f1.vn = 1; f1.tuple = 1;
-    if (m->fmask) {
-#define X(T, OP) k_fused_sell_w<T, OP, 4, true><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, transpose)
-      FOR_DOM_W(X)
+    /* weighted gs: float/double fields (checked by the caller) */
+    if (mode == XM_PLAIN || f->vn == 1) {
+      xcu_field f1 = *f;
+      f1.vn = 1; f1.tuple = 1;
+      if (m->fmask) {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_PLAIN, 1, 4, true, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, transpose)
+        FOR_DOM_W(X)
 #undef X
+      } else {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_PLAIN, 1, 4, false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, 0)
+        FOR_DOM_W(X)
+#undef X
+      }
+    } else if (mode == XM_VEC) {
+      if (m->fmask) {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_VEC, 1, 4, true, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), (const T *)f->w, transpose)
+        FOR_DOM_W(X)
+#undef X
+      } else {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 2 : 3), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), (const T *)f->w, 0)
+        FOR_DOM_W(X)
+#undef X
+      }
     } else {
-#define X(T, OP) k_fused_sell_w<T, OP, 4, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), (const T *)f->w, 0)
-      FOR_DOM_W(X)
+      if (m->fmask) {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_MANY, 1, 4, true, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, transpose)
+        FOR_DOM_W(X)
 #undef X
+      } else {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 3), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, 0)
+        FOR_DOM_W(X)
+#undef X
+      }
     }
     LAUNCHED();
     return;
@@ -946,14 +983,10 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
     xcu_field f1 = *f;
     f1.vn = 1; f1.tuple = 1;
     mode = XM_PLAIN;
-    /* 4-byte elements: 8 resident CTAs per SM (32 registers, no spills) */
+    /* 6 resident CTAs per SM: 8 (32 registers, no spills) was measured in round 2 and is
+       no faster for 4-byte elements and 3 % slower for 8-byte ones (profiles/r2_knobs_occupancy_line_shift.txt) */
 #define X(T, OP, MODE)                                                        \
-  do {                                                                        \
-    if (m->occ ? m->occ >= 8 : sizeof(T) == 4)                                \
-      k_fused_sell<T, OP, XM_PLAIN, 1, 8><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0); \
-    else                                                                      \
-      k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0); \
-  } while (0)
+  k_fused_sell<T, OP, XM_PLAIN, 1, 6><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_PLAIN>(&f1), 0)
     FOR_DOM(XM_PLAIN, X)
 #undef X
   } else if (mode == XM_VEC && f->vn == 3 && f->tuple == 3 && f->k0 == 0 &&
@@ -1102,7 +1135,12 @@ void xcu_bnd_unpack(void *stream, const xcu_bnd *b, const xcu_field *f, int mode
   if (!b->nb) return;
   cudaStream_t st = (cudaStream_t)stream;
   if (f->w) {
-#define X(T, OP) k_bnd_unpack_w<T, OP><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, (T *)f->p[0], (const T *)f->w, transpose, (const T *)recvbuf, allreduce, depoch, par_bytes)
+#define X(T, OP)                                                              \
+  do {                                                                        \
+    if (mode == XM_PLAIN) k_bnd_unpack_w<T, OP, XM_PLAIN><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, make_fld<T, XM_PLAIN>(f), (const T *)f->w, transpose, (const T *)recvbuf, bufvn, allreduce, depoch, par_bytes); \
+    else if (mode == XM_VEC) k_bnd_unpack_w<T, OP, XM_VEC><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, make_fld<T, XM_VEC>(f), (const T *)f->w, transpose, (const T *)recvbuf, bufvn, allreduce, depoch, par_bytes); \
+    else k_bnd_unpack_w<T, OP, XM_MANY><<<bnd_blocks(b->nb), 256, 0, st>>>(*b, make_fld<T, XM_MANY>(f), (const T *)f->w, transpose, (const T *)recvbuf, bufvn, allreduce, depoch, par_bytes); \
+  } while (0)
     FOR_DOM_W(X)
 #undef X
     LAUNCHED();

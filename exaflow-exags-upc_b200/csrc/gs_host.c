@@ -79,14 +79,6 @@ struct gs_data {
 };
 
 /* ------------------------------------------------------------------ */
-/* EXAGS_SELL_OCC=6|8 (read at gs_setup, for A/B runs): resident CTAs per SM of
-   the plain sliced kernel; unset: 8 for 4-byte elements, 6 for 8-byte ones    */
-static u32 sell_occ(void)
-{
-  const char *e = getenv("EXAGS_SELL_OCC");
-  return e ? (u32)atoi(e) : 0u;
-}
-
 static void *upload(const void *src, size_t bytes)
 {
   void *d = xcu_malloc(bytes);
@@ -790,9 +782,10 @@ void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op, unsigned tr
 
 /* Weighted gs (extension, include/exags_cuda.h): what Nek issues
    as dssum followed by a multiplication with the inverse multiplicity, in the
-   one pass over the field that gs makes anyway.  Device vectors, plain
-   float/double fields, transpose 0.                                          */
-static void gs_run_weighted(void *u, const void *wgt, int dom, int op, struct gs_data *g,
+   one pass over the field that gs makes anyway.  Device vectors, float/double
+   fields -- plain, T[n][vn] (one weight per node for all its components, as
+   for a velocity field) or vn arrays -- transpose 0.                          */
+static void gs_run_weighted(void *u, int mode, unsigned vn, const void *wgt, int dom, int op, struct gs_data *g,
                             void *stream, int blocking, const char *who)
 {
   int xd;
@@ -802,20 +795,34 @@ static void gs_run_weighted(void *u, const void *wgt, int dom, int op, struct gs
   if (op > XO_MAX) xfail("%s: op %d not in valid range", who, op);
   if (!g->on_device)
     xfail("%s: no CUDA device -- this library has no CPU execution path", who);
-  if (!g->n) return;
-  if (blocking && (!xcu_is_device_ptr(u) || !xcu_is_device_ptr(wgt)))
-    xfail("%s: u and w must be device vectors", who);
-  if (blocking) stream = xg_world_stream(g->w, 0);
-  void *ptrs[1] = { u };
-  gs_enqueue(g, ptrs, XM_PLAIN, 1, xd, op, 0, stream, wgt);
+  if (!g->n || !vn) return;
+  void *ptrs_few[XG_MAXV];
+  void **ptrs = vn <= XG_MAXV || mode != XM_MANY ? ptrs_few : xnew(void *, vn);
+  if (mode == XM_MANY) for (unsigned k = 0; k < vn; ++k) ptrs[k] = ((void *const *)u)[k];
+  else ptrs[0] = u;
+  if (blocking) {
+    if (!xcu_is_device_ptr(wgt)) xfail("%s: u and w must be device vectors", who);
+    for (unsigned k = 0; k < (mode == XM_MANY ? vn : 1u); ++k)
+      if (!xcu_is_device_ptr(ptrs[k])) xfail("%s: u and w must be device vectors", who);
+    stream = xg_world_stream(g->w, 0);
+  }
+  gs_enqueue(g, ptrs, mode, vn, xd, op, 0, stream, wgt);
   if (blocking) { xcu_stream_sync(stream); push_check(g, "during this call"); }
+  if (ptrs != ptrs_few) free(ptrs);
 }
 
 void exags_gs_weighted(void *u, const void *w, int dom, int op, struct gs_data *gsh)
-{ gs_run_weighted(u, w, dom, op, gsh, 0, 1, "gs_weighted"); }
-
+{ gs_run_weighted(u, XM_PLAIN, 1, w, dom, op, gsh, 0, 1, "gs_weighted"); }
 void exags_gs_weighted_async(void *u, const void *w, int dom, int op, struct gs_data *gsh, void *stream)
-{ gs_run_weighted(u, w, dom, op, gsh, stream, 0, "gs_weighted_async"); }
+{ gs_run_weighted(u, XM_PLAIN, 1, w, dom, op, gsh, stream, 0, "gs_weighted_async"); }
+void exags_gs_weighted_vec(void *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh)
+{ gs_run_weighted(u, XM_VEC, vn, w, dom, op, gsh, 0, 1, "gs_weighted_vec"); }
+void exags_gs_weighted_vec_async(void *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh, void *stream)
+{ gs_run_weighted(u, XM_VEC, vn, w, dom, op, gsh, stream, 0, "gs_weighted_vec_async"); }
+void exags_gs_weighted_many(void *const *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh)
+{ gs_run_weighted((void *)u, XM_MANY, vn, w, dom, op, gsh, 0, 1, "gs_weighted_many"); }
+void exags_gs_weighted_many_async(void *const *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh, void *stream)
+{ gs_run_weighted((void *)u, XM_MANY, vn, w, dom, op, gsh, stream, 0, "gs_weighted_many_async"); }
 
 /* the Nek flavour shares the operator; only the id width differs */
 void gslib_gs(void *u, int dom, int op, unsigned t, struct gs_data *g, buffer *b)
@@ -951,8 +958,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   }
   if (g->on_device && use_sell) {
     upload_csr(&g->d_int, &sell.rest);
-    g->d_sell.occ = sell_occ();
-      g->d_sell.nblock = sell.nblock;
+        g->d_sell.nblock = sell.nblock;
     g->d_sell_mem[0] = upload(sell.mask, (size_t)sell.nblock * 32 + 1);
     g->d_sell_mem[1] = upload(sell.idx, (sell.nidx ? sell.nidx : 1) * sizeof(u32));
     g->d_sell.mask = (const unsigned char *)g->d_sell_mem[0]; g->d_sell.idx = (const u32 *)g->d_sell_mem[1];
@@ -1103,7 +1109,6 @@ static void adopt_interior(struct gs_data *g, const struct xcu_dmap *in, const s
 {
   struct xcu_dsell ds;
   xcu_setup_sell(in, &ds);
-  g->d_sell.occ = sell_occ();
   g->d_sell.nblock = ds.nblock;
   g->d_sell.mask = ds.mask; g->d_sell.idx = ds.idx; g->d_sell.fmask = ds.fmask;
   g->d_sell_mem[0] = ds.mask; g->d_sell_mem[1] = ds.idx; g->d_sell_mem[2] = ds.fmask;

@@ -92,6 +92,11 @@ def lib() -> C.CDLL:
     L.exags_gs_weighted.restype = None
     L.exags_gs_weighted_async.argtypes = [vp, vp, i32, i32, vp, vp]
     L.exags_gs_weighted_async.restype = None
+    for name in ("exags_gs_weighted_vec", "exags_gs_weighted_many"):
+        getattr(L, name).argtypes = [vp, u32, vp, i32, i32, vp]
+        getattr(L, name).restype = None
+        getattr(L, name + "_async").argtypes = [vp, u32, vp, i32, i32, vp, vp]
+        getattr(L, name + "_async").restype = None
     L.gslib_gs_free.argtypes = [vp]
     L.exags_gs_free.argtypes = [vp]
     L.gslib_gs_unique.argtypes = [vp, u32, comm_ptr]
@@ -232,6 +237,23 @@ def gs_weighted(u, w, dom: int, op: int, gsh: GS, stream: int | None = None) -> 
         lib().exags_gs_weighted(_addr(u), _addr(w), dom, op, gsh.ptr)
     else:
         lib().exags_gs_weighted_async(_addr(u), _addr(w), dom, op, gsh.ptr, stream)
+
+
+def gs_weighted_vec(u, vn: int, w, dom: int, op: int, gsh: GS, stream: int | None = None) -> None:
+    """u[i][k] <- w[i] * gs_vec(u, op)[i][k] in one pass (include/exags_cuda.h); device vectors."""
+    if stream is None:
+        lib().exags_gs_weighted_vec(_addr(u), vn, _addr(w), dom, op, gsh.ptr)
+    else:
+        lib().exags_gs_weighted_vec_async(_addr(u), vn, _addr(w), dom, op, gsh.ptr, stream)
+
+
+def gs_weighted_many(us, vn: int, w, dom: int, op: int, gsh: GS, stream: int | None = None) -> None:
+    """us[k][i] <- w[i] * gs_many(us, op)[k][i] in one pass (include/exags_cuda.h); device vectors."""
+    tab = (C.c_void_p * vn)(*[_addr(x) for x in us[:vn]])
+    if stream is None:
+        lib().exags_gs_weighted_many(C.addressof(tab), vn, _addr(w), dom, op, gsh.ptr)
+    else:
+        lib().exags_gs_weighted_many_async(C.addressof(tab), vn, _addr(w), dom, op, gsh.ptr, stream)
 
 
 def gs_free(gsh: GS) -> None:

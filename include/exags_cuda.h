@@ -36,6 +36,16 @@ void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op,
 void exags_gs_weighted(void *u, const void *w, int dom, int op, struct gs_data *gsh);
 void exags_gs_weighted_async(void *u, const void *w, int dom, int op,
                              struct gs_data *gsh, void *stream);
+/* The same for gs_vec fields T[n][vn] and gs_many fields (host table of vn
+   device pointers): one weight per node, w[i], applies to all vn components of
+   node i -- the velocity field of a Nek step.  Equal, bit for bit, to vn
+   weighted plain calls.                                                      */
+void exags_gs_weighted_vec(void *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh);
+void exags_gs_weighted_vec_async(void *u, unsigned vn, const void *w, int dom, int op,
+                                 struct gs_data *gsh, void *stream);
+void exags_gs_weighted_many(void *const *u, unsigned vn, const void *w, int dom, int op, struct gs_data *gsh);
+void exags_gs_weighted_many_async(void *const *u, unsigned vn, const void *w, int dom, int op,
+                                  struct gs_data *gsh, void *stream);
 
 /* Stream-ordered comm_dot (src/comm.upc:954-959 on device vectors): *d_out =
    sum over all ranks of sum_i v[i]*w[i], left in device memory and ordered on

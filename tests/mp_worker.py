@@ -258,6 +258,25 @@ def main():
                         bad = np.flatnonzero(outs[r] != w_r)
                         print(f"MISMATCH execw case={case} {np.dtype(dt).name} {op} rank={r}: {bad.size} differ, first {bad[:5]}")
                         ok = False
+            # a 3-component field with the same weights: equal to three plain weighted calls
+            comps = [cases.values(ids.size, dt, op, 1000 * rank + 40 + k) for k in range(3)]
+            want3 = []
+            for c in comps:
+                d3 = torch.from_numpy(c.copy()).cuda()
+                X.gs_weighted(d3, dw, dom, opi, g)
+                want3.append(d3)
+            many = [torch.from_numpy(c.copy()).cuda() for c in comps]
+            X.gs_weighted_many(many, 3, dw, dom, opi, g)
+            vec = torch.from_numpy(np.stack(comps, axis=1).reshape(-1).copy()).cuda()
+            X.gs_weighted_vec(vec, 3, dw, dom, opi, g)
+            same = all(torch.equal(a, b) for a, b in zip(many, want3)) and \
+                torch.equal(vec.view(ids.size, 3), torch.stack(want3, dim=1))
+            if method in (0, 3) and op in ("add", "mul") and not same:    # all-reduce method: NCCL's association
+                same = all(np.allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5) for a, b in zip(many, want3))
+            if not same:
+                print(f"MISMATCH execw vec/many case={case} {np.dtype(dt).name} {op} rank={rank}")
+                ok = False
+            okt = torch.tensor([1 if ok else 0]); dist.all_reduce(okt, op=dist.ReduceOp.MIN); ok = bool(okt.item())
     elif what == "execg":
         # np > 1 under a CUDA graph (push transport): the exchange number lives in
         # the mailbox header on the device, so the captured pack / wait / unpack

@@ -526,6 +526,33 @@ def test_weighted_gs(X, O, kind):
     X.gs_free(g)
 
 
+@pytest.mark.parametrize("kind", ["sem", "random_flagged", "long_groups"])
+def test_weighted_gs_vec_many(X, kind):
+    """exags_gs_weighted_vec / _many (one weight per node for all components, a
+    velocity field): bit for bit what vn weighted plain calls give -- and those are
+    checked against the oracle in test_weighted_gs."""
+    ids = {"sem": semmesh.box_ids(5, 4, 3, 7), "random_flagged": cases.random_ids(6000, 900, 5),
+           "long_groups": cases.random_ids(4000, 60, 6, p_flag=0.0, long_group=50)}[kind]
+    n = ids.size
+    g = X.gs_setup(ids)
+    for dt, vn, op in itertools.product((np.float64, np.float32), (2, 3, 5), ("add", "max")):
+        dom, opi = X.NP_DOM[np.dtype(dt)], cases.OPS.index(op)
+        comps = [cases.values(n, dt, op, 30 + k) for k in range(vn)]
+        w = _dev(np.random.default_rng(8).uniform(0.25, 1.0, n).astype(dt))
+        want = []
+        for c in comps:
+            d = _dev(c)
+            X.gs_weighted(d, w, dom, opi, g)
+            want.append(d)
+        many = [_dev(c) for c in comps]
+        X.gs_weighted_many(many, vn, w, dom, opi, g)
+        assert all(torch.equal(a, b) for a, b in zip(many, want)), (kind, dt, vn, op, "many")
+        vec = _dev(np.stack(comps, axis=1).reshape(-1))
+        X.gs_weighted_vec(vec, vn, w, dom, opi, g)
+        assert torch.equal(vec.view(n, vn), torch.stack(want, dim=1)), (kind, dt, vn, op, "vec")
+    X.gs_free(g)
+
+
 def test_weighted_gs_is_dsavg(X):
     """With w = 1 / multiplicity the weighted sum is the average over the copies
     of a node: a field that is already continuous is reproduced exactly."""

@@ -1,7 +1,6 @@
 """A/B timing on M7 of the knobs that are read at gs_setup time, one handle per setting, interleaved
 so that drift hits every setting alike:  python tools/knob_bench.py
     EXAGS_SELL_LINE_SHIFT=4|5|6   chain ordering on 16/32/64-element lines (default 5)
-    EXAGS_SELL_OCC=6|8            resident CTAs per SM of the plain kernel (default: 8 for 4-byte, 6 for 8-byte)
 for plain gs on double / float / int, gs_vec(3) and gs_many(3) in float and double, the weighted gs, and
 a unique=1 handle (both transposes)."""
 import json
@@ -21,7 +20,7 @@ except Exception:
     pass
 ids = semmesh.box_ids(64, 64, 48, 7)
 n = ids.size
-KNOBS = ("EXAGS_SELL_LINE_SHIFT", "EXAGS_SELL_OCC")
+KNOBS = ("EXAGS_SELL_LINE_SHIFT",)
 
 
 def handle(unique=0, **env):
@@ -34,8 +33,7 @@ def handle(unique=0, **env):
     return g
 
 
-H = {"line_shift=5": handle(), "line_shift=4": handle(EXAGS_SELL_LINE_SHIFT=4), "line_shift=6": handle(EXAGS_SELL_LINE_SHIFT=6),
-     "occ=6": handle(EXAGS_SELL_OCC=6), "occ=8": handle(EXAGS_SELL_OCC=8)}
+H = {"line_shift=5": handle(), "line_shift=4": handle(EXAGS_SELL_LINE_SHIFT=4), "line_shift=6": handle(EXAGS_SELL_LINE_SHIFT=6)}
 info = H["line_shift=5"].info()
 G, S, nsec = info["groups"], info["members"], info["sectors_f64"]
 stream = torch.cuda.current_stream().cuda_stream

@@ -37,6 +37,7 @@ ap.add_argument("--order", type=int, default=9)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--no-check", action="store_true")
 ap.add_argument("--out", default="")
+ap.add_argument("--only", default="", help="run just this case, e.g. add,double")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -112,6 +113,8 @@ for dom in (X.gs_double, X.gs_float, X.gs_int, X.gs_long):
     tdt, ndt = DT[dom]
     for op in (X.gs_add, X.gs_mul, X.gs_min, X.gs_max):
         opname = OPS[op][0]
+        if args.only and args.only != f"{opname},{NAMES[dom]}":
+            continue
         u0 = make_field(tdt, opname)
         u = u0.clone()
         X.gs_async(u, X.mode_plain, 1, dom, op, 0, g, stream)
