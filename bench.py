@@ -435,6 +435,11 @@ def run_gpu(args) -> None:
             except Exception as exc:
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"cpu baseline failed: {exc}"}
         nvlink = None
+        if world > 1:
+            nvlink = {"counters": "NVML reports the NVLink throughput counters as not supported on this box; "
+                                  "ncu's nvltx/nvlrx bytes of the send kernel are in profiles/r2_ncu_nvlink_k_pack_slots.txt",
+                      "payload_bytes_sent_per_rank_per_step": 8 * info["send_slots"],
+                      "peak_GBps_per_direction": 900.0}
         if nvl0 is not None and nvl1 is not None:
             # rank 0's GPU over the timed region (it also carries the barrier's few bytes of NCCL traffic);
             # the exchange occupies the link for the length of the pack kernel, a few tens of microseconds

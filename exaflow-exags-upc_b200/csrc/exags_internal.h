@@ -364,7 +364,8 @@ void xcu_setup_local(const struct xcu_topo *t, struct xcu_dmap *hall, struct xcu
 void xcu_setup_split(const struct xcu_topo *t, const u32 *bgrp_host, u32 nb, struct xcu_dmap *hall,
                      struct xcu_dmap *in, struct xcu_dmap *bnd, struct xcu_dmap *bnd2,
                      u32 **fp, u32 *nfp, u32 **fs, u32 *nfs, u64 *sectors);
-void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s);
+int  xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s);   /* 1: too large for the sliced layout */
+void xcu_dmap_clone(const struct xcu_dmap *m, struct xcu_dmap *out);
 void xcu_dmap_free(struct xcu_dmap *m);
 void xcu_dmap_to_host(const struct xcu_dmap *m, struct xg_hmap *h);
 void xcu_note_launches(unsigned long long k);

@@ -1108,7 +1108,16 @@ static void topo_any(struct gs_data *g, struct xg_topo *topo, const void *id, in
 static void adopt_interior(struct gs_data *g, const struct xcu_dmap *in, const struct xcu_dmap *bnd)
 {
   struct xcu_dsell ds;
-  xcu_setup_sell(in, &ds);
+  if (xcu_setup_sell(in, &ds)) {
+    /* beyond the sliced layout's size limits (2^30 member indices or 2^23
+       blocks): the thread-per-group CSR kernel (k_fused) serves the whole map */
+    struct xcu_dmap own;
+    xcu_dmap_clone(in, &own);
+    g->d_int.c.ng = own.ng; g->d_int.c.ni = own.ni;
+    g->d_int.off = own.off; g->d_int.idx = own.idx; g->d_int.nunf = own.nunf;
+    g->d_int.c.off = own.off; g->d_int.c.idx = own.idx; g->d_int.c.nunf = own.nunf;
+    return;
+  }
   g->d_sell.nblock = ds.nblock;
   g->d_sell.mask = ds.mask; g->d_sell.idx = ds.idx; g->d_sell.fmask = ds.fmask;
   g->d_sell_mem[0] = ds.mask; g->d_sell_mem[1] = ds.idx; g->d_sell_mem[2] = ds.fmask;
@@ -1195,7 +1204,7 @@ static void split_groups_device(struct gs_data *g, const struct xcu_topo *dt)
     if (!dt->any_flag && !(bf && atoi(bf) == 0)) {
       if (bnd2.ng) {
         struct xcu_dsell bs;
-        xcu_setup_sell(&bnd2, &bs);
+        if (xcu_setup_sell(&bnd2, &bs)) xfail("gs_setup: boundary map too large for the sliced layout");
         g->d_brest.c.ng = bs.rest.ng; g->d_brest.c.ni = bs.rest.ni;
         g->d_brest.off = bs.rest.off; g->d_brest.idx = bs.rest.idx; g->d_brest.nunf = bs.rest.nunf;
         g->d_brest.c.off = bs.rest.off; g->d_brest.c.idx = bs.rest.idx; g->d_brest.c.nunf = bs.rest.nunf;

@@ -358,11 +358,41 @@ void xcu_setup_bgrp(const struct xcu_topo *t, const u32 *bprim, u32 nb, u32 *bgr
   be.release(d_p); be.release(d_g);
 }
 
-void xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
+/* returns 1 when the map is too large for the sliced layout (2^30 members or
+   2^23 blocks; s is then empty and the caller keeps the map in CSR form), else 0 */
+int xcu_setup_sell(const struct xcu_dmap *m, struct xcu_dsell *s)
 {
   Scope sc; CudaBackend &be = sc.be;
-  check(xgsetup::sell_build(be, m, s, xg_sell_pairs_enabled()), "sliced layout");
+  /* EXAGS_SELL_MAX_MEMBERS lowers the limit so that the CSR fallback can be exercised on a small map (tests) */
+  const char *lim = getenv("EXAGS_SELL_MAX_MEMBERS");
+  int rc = (lim && (size_t)m->ni >= (size_t)atoll(lim)) ? (int)xgsetup::ERR_SELL_TOO_LARGE : (int)xgsetup::OK;
+  if (rc == xgsetup::OK) rc = xgsetup::sell_build(be, m, s, xg_sell_pairs_enabled());
+  else memset(s, 0, sizeof *s);
+  if (rc == xgsetup::ERR_SELL_TOO_LARGE) {
+    xgsetup::sell_release(be, s);
+    memset(s, 0, sizeof *s);
+    CU(cudaStreamSynchronize(be.st));
+    return 1;
+  }
+  check(rc, "sliced layout");
   CU(cudaStreamSynchronize(be.st));
+  return 0;
+}
+
+/* a copy of a device CSR map that the handle owns */
+void xcu_dmap_clone(const struct xcu_dmap *m, struct xcu_dmap *out)
+{
+  memset(out, 0, sizeof *out);
+  out->ng = m->ng; out->ni = m->ni;
+  if (!m->ng) return;
+  out->off = (u32 *)xcu_malloc(((size_t)m->ng + 1) * sizeof(u32));
+  out->idx = (u32 *)xcu_malloc(((size_t)m->ni + 1) * sizeof(u32));
+  CU(cudaMemcpy(out->off, m->off, ((size_t)m->ng + 1) * sizeof(u32), cudaMemcpyDeviceToDevice));
+  CU(cudaMemcpy(out->idx, m->idx, (size_t)m->ni * sizeof(u32), cudaMemcpyDeviceToDevice));
+  if (m->nunf) {
+    out->nunf = (u32 *)xcu_malloc(((size_t)m->ng + 1) * sizeof(u32));
+    CU(cudaMemcpy(out->nunf, m->nunf, (size_t)m->ng * sizeof(u32), cudaMemcpyDeviceToDevice));
+  }
 }
 
 void xcu_dmap_free(struct xcu_dmap *m)

@@ -267,6 +267,27 @@ def test_config3_full_size(X, dt):
     X.gs_free(g)
 
 
+def test_map_too_large_for_sliced_layout_falls_back_to_csr(X, O, monkeypatch):
+    """Beyond the sliced layout's size limits (2^30 member indices) gs_setup keeps
+    the map in CSR form and the thread-per-group kernel serves it; the limit is
+    lowered here so that a small map takes that path."""
+    ids = cases.random_ids(4000, 700, 12)
+    monkeypatch.setenv("EXAGS_SELL_MAX_MEMBERS", "100")
+    g, o = X.gs_setup(ids), O.Oracle([ids])
+    monkeypatch.delenv("EXAGS_SELL_MAX_MEMBERS")
+    assert g.info()["sell_entries"] == 0 and g.info()["interior_groups"] > 0
+    for (dname, dt), op, t, (mode, vn) in itertools.product(cases.DTYPES.items(), ("add", "min"), (0, 1),
+                                                             ((0, 1), (1, 3), (2, 3))):
+        got, want = _run_both(X, O, g, o, dt, op, t, mode, vn, ids.size, 5)
+        assert np.array_equal(got, want), (dname, op, t, mode)
+    host = cases.values(ids.size, np.float64, "add", 9)
+    want = host.copy()
+    o.exec([want], O.M_PLAIN, 1, O.D_DOUBLE, O.O_ADD, 0)
+    X.gs(host, X.gs_double, X.gs_add, 0, g)
+    assert np.array_equal(host, want)
+    X.gs_free(g)
+
+
 def test_fortran_bindings(X):
     """fgs_setup / gs_op / gs_op_vec / gs_op_many / gs_op_fields / gs_free by reference
     (src/gs.upc:1309-1418), Nek flavour: dom 1..3, op 1..4, 0-based handles."""

@@ -50,8 +50,11 @@ def sector_counts(handle, esz, vn_tuple, transpose):
     """(sectors read, sectors written, members, groups, flagged singles) of one call on a T[n][vn_tuple]
     field, from the handle's own sentinel maps: map 1 = every group in full, map 0 = unflagged members only.
     transpose 0 reads map 0's members and writes map 1's; transpose 1 the other way round."""
-    def members_of(which):
+    def members_of(which, heads=False):
         m = torch.from_numpy(handle.dump_map(which).astype(np.int64)).cuda()
+        if heads:                                     # first entry of every group: the primaries
+            prev = torch.cat([torch.tensor([NIL], device="cuda"), m[:-1]])
+            return m[(prev == NIL) & (m != NIL)]
         return m[m != NIL], int((m == NIL).sum().item()) - 1
 
     def nsec(idx):
@@ -73,8 +76,9 @@ def sector_counts(handle, esz, vn_tuple, transpose):
     fp = fp[fp != NIL]
     # a store into a sector makes DRAM read it first (32-byte ECC granularity) unless the whole sector is
     # written, so the sectors read are those of every member touched at all; written: those of the stored ones
+    # transpose 1: the gather over map 1 writes every primary, the scatter over map 0 the unflagged members
     touched = torch.cat([full, fp])
-    wr = touched if not transpose else unf
+    wr = touched if not transpose else torch.cat([members_of(1, heads=True), unf])
     return nsec(touched), nsec(wr), full.numel(), G, info["flagged_singles"]
 
 
