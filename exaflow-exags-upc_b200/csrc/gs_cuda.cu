@@ -247,7 +247,7 @@ __device__ __forceinline__ unsigned swap_pair_bits(unsigned m, unsigned ph)
 // to a member is the group's result times wgt[member]; the weights are fetched
 // together with the field so that both loads are in flight at once.
 template <typename T, int OP, int MODE, int KU, bool GONLY = false, bool FLG = false, bool ONE = false,
-          bool WGT = false>
+          int WGT = 0>
 __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, const uint4 b,
                                           const unsigned startph, const unsigned flg = 0u,
                                           const int transpose = 0, const T *__restrict__ wgt = nullptr)
@@ -298,12 +298,16 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
         for (int j = 0; j < 8; ++j)
           if ((lld >> j) & 1u) x[kk][j] = pk[kk][id[j] * es];
       }
+    // WGT == 1: the weights are fetched together with the field (both loads in
+    // flight at once); WGT == 2: after the reduction, just ahead of the stores --
+    // they then occupy no registers across it, which is what the three-component
+    // float kernels need to keep four CTAs on an SM without spilling.
+    // A one-member group (a flagged single: start bit, next slot empty) is no
+    // group result -- gs_init's identity goes there unweighted.  Such a lane
+    // slot has no phase, so slot order and fetch order agree for it.
+    const unsigned lw = WGT ? (FLG ? lout & ~(start & ~(mem >> 1)) : lout) : 0u;
     T wv[WGT ? 8 : 1];
-    if (WGT) {
-      // a one-member group (a flagged single: start bit, next slot empty) is no
-      // group result -- gs_init's identity goes there unweighted.  Such a lane
-      // slot has no phase, so slot order and fetch order agree for it.
-      const unsigned lw = FLG ? lout & ~(start & ~(mem >> 1)) : lout;
+    if (WGT == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         wv[WGT ? j : 0] = (T)1;
@@ -344,6 +348,13 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
         x[kk][j] = sw ? p1 : p0; x[kk][j + 1] = sw ? p0 : p1;
       }
     }
+    if (WGT == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wv[WGT ? j : 0] = (T)1;
+        if ((lw >> j) & 1u) wv[WGT ? j : 0] = __ldg(wgt + id[j]);
+      }
+    }
 #pragma unroll
     for (int kk = 0; kk < KU; ++kk)
       if (KU == 1 || k0 + kk < f.vn) {
@@ -372,7 +383,7 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
 // float/double fields.  One weight per member is read (it applies to every
 // component of a vector field), against a separate pass over the whole field
 // (read u, read w, write u).
-template <typename T, int OP, int MODE, int KU, int MINB, bool FLG, bool ONE>
+template <typename T, int OP, int MODE, int KU, int MINB, bool FLG, bool ONE, int WL = 1>
 __global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
 k_fused_sell_w(xcu_sell m, Fld<T, MODE> f, const T *__restrict__ wgt, int transpose)
 {
@@ -382,7 +393,7 @@ k_fused_sell_w(xcu_sell m, Fld<T, MODE> f, const T *__restrict__ wgt, int transp
   const uint4 a = __ldg(p), b = __ldg(p + 1);
   const unsigned start = __ldg(m.mask + (size_t)c * 32u + lane);
   const unsigned flg = FLG ? __ldg(m.fmask + (size_t)c * 32u + lane) : 0u;
-  sell_lane<T, OP, MODE, KU, false, FLG, ONE, true>(f, a, b, start, flg, transpose, wgt);
+  sell_lane<T, OP, MODE, KU, false, FLG, ONE, WL>(f, a, b, start, flg, transpose, wgt);
 }
 
 template <typename T, int OP, int MODE>
@@ -959,7 +970,7 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
         FOR_DOM_W(X)
 #undef X
       } else {
-#define X(T, OP) k_fused_sell_w<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 2 : 3), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), (const T *)f->w, 0)
+#define X(T, OP) k_fused_sell_w<T, OP, XM_VEC, 3, (sizeof(T) == 8 ? 2 : 4), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_VEC>(f), (const T *)f->w, 0)
         FOR_DOM_W(X)
 #undef X
       }
@@ -969,9 +980,17 @@ void xcu_fused_sell(void *stream, const xcu_sell *m, const xcu_field *f, int mod
         FOR_DOM_W(X)
 #undef X
       } else {
-#define X(T, OP) k_fused_sell_w<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 3), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, 0)
-        FOR_DOM_W(X)
+        /* up to three arrays: component numbers are compile-time constants (ONE), so the
+           pointer table is read with constant indices -- see Fld::comp */
+        if (f->vn <= 3) {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 4), false, true, (sizeof(T) == 8 ? 1 : 2)><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, 0)
+          FOR_DOM_W(X)
 #undef X
+        } else {
+#define X(T, OP) k_fused_sell_w<T, OP, XM_MANY, 3, (sizeof(T) == 8 ? 2 : 3), false, false><<<grid, nthr, 0, st>>>(*m, make_fld<T, XM_MANY>(f), (const T *)f->w, 0)
+          FOR_DOM_W(X)
+#undef X
+        }
       }
     }
     LAUNCHED();

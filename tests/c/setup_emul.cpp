@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <set>
 #include <vector>
 #include "setup_pipeline.h"
 
@@ -344,4 +345,74 @@ extern "C" size_t setup_emul_sell_dump(const void *id, int idbytes, size_t n, u3
   }
   xg_sell_free(&hs); xg_hmap_free(&hh); xg_topo_free(&ht);
   return nb;
+}
+
+// The candidate filters of the np > 1 setup (setup_pipeline.h: cand_bins, cand_from_bins,
+// cand_presence, cand_refine, cand_compact, groups_of_primaries) for two label sets standing in
+// for two ranks.  What must hold whatever the hash does: a label both ranks hold is a candidate on
+// rank A (the filters only err towards sending); every candidate row is (|label|, primary index,
+// complemented when the primary is flagged) of its group, in group order; and every primary is
+// found again by the group lookup.  Returns 0, or a code naming the first violated property.
+extern "C" int setup_emul_candidates(const void *idA, size_t nA, const void *idB, size_t nB, int idbytes, int reverse)
+{
+  HostBackend be;
+  be.reverse = reverse != 0;
+  xcu_topo ta, tb;
+  if (xgsetup::topo_build(be, idA, idbytes, nA, &ta, (u64 *)0)) return 10;
+  if (xgsetup::topo_build(be, idB, idbytes, nB, &tb, (u64 *)0)) return 11;
+  u64 gmax = 0;
+  for (size_t g = 0; g < ta.ngrp; ++g) gmax = std::max(gmax, ta.id[g]);
+  for (size_t g = 0; g < tb.ngrp; ++g) gmax = std::max(gmax, tb.id[g]);
+  unsigned shift = 0;
+  while ((gmax >> shift) >= (u64)xgsetup::CAND_BINS) ++shift;
+  const size_t bw = xgsetup::CAND_BINS / 32;
+  std::vector<u32> binsA(bw, 0), binsB(bw, 0);
+  xgsetup::cand_bins(be, &ta, shift, binsA.data());
+  xgsetup::cand_bins(be, &tb, shift, binsB.data());
+  std::vector<u32> cA(ta.ngrp + 1), cB(tb.ngrp + 1);
+  xgsetup::cand_from_bins(be, &ta, shift, binsB.data(), cA.data());
+  xgsetup::cand_from_bins(be, &tb, shift, binsA.data(), cB.data());
+  const u64 maxn = std::max<u64>(1, std::max(be.sum_u32(cA.data(), ta.ngrp), be.sum_u32(cB.data(), tb.ngrp)));
+  unsigned bits = 20;
+  while (bits < 34 && ((u64)1 << bits) < 16 * maxn) ++bits;
+  const size_t words = (size_t)1 << (bits - 5);
+  std::vector<u32> bmA(words, 0), bmB(words, 0);
+  xgsetup::cand_presence(be, &ta, cA.data(), bits, bmA.data());
+  xgsetup::cand_presence(be, &tb, cB.data(), bits, bmB.data());
+  xgsetup::cand_refine(be, &ta, cA.data(), bits, bmB.data());
+  std::vector<u32> flagged(cA.begin(), cA.end());     // cand_compact consumes its input
+  u64 *cid = 0; u32 *csf = 0;
+  const u32 cnt = xgsetup::cand_compact(be, &ta, cA.data(), &cid, &csf);
+  int out = 0;
+  std::set<u64> inB(tb.id, tb.id + tb.ngrp);
+  u32 o = 0;
+  for (size_t g = 0; g < ta.ngrp && !out; ++g) {
+    const bool is_cand = flagged[g] != 0;
+    if (inB.count(ta.id[g]) && !is_cand) out = 20;                 // a shared label was dropped
+    if (!is_cand) continue;
+    if (o >= cnt) { out = 21; break; }
+    const u32 a = ta.gstart[g];
+    if (cid[o] != ta.id[g] || csf[o] != (ta.flag[a] ? ~ta.idx[a] : ta.idx[a])) out = 22;
+    ++o;
+  }
+  if (!out && o != cnt) out = 23;
+  if (!out && ta.ngrp) {
+    std::vector<u32> prim(ta.ngrp), grp(ta.ngrp);
+    for (size_t g = 0; g < ta.ngrp; ++g) prim[g] = ta.idx[ta.gstart[g]];
+    xgsetup::groups_of_primaries(be, &ta, prim.data(), (u32)ta.ngrp, grp.data());
+    for (size_t g = 0; g < ta.ngrp; ++g) if (grp[g] != (u32)g) { out = 24; break; }
+    u32 none_in = (u32)nA, none_out = 0;                           // an index that heads no group
+    for (u32 i = 0; i < (u32)nA; ++i) {
+      bool heads = false;
+      for (size_t g = 0; g < ta.ngrp; ++g) if (prim[g] == i) { heads = true; break; }
+      if (!heads) { none_in = i; break; }
+    }
+    if (none_in < (u32)nA) {
+      xgsetup::groups_of_primaries(be, &ta, &none_in, 1, &none_out);
+      if (none_out != XG_NONE) out = 25;
+    }
+  }
+  be.release(cid); be.release(csf);
+  xgsetup::topo_release(be, &ta); xgsetup::topo_release(be, &tb);
+  return out;
 }

@@ -47,6 +47,9 @@ def emul():
         bgrp = np.flatnonzero(rng.random(ng) < frac).astype(np.uint32)
         return L.setup_emul_split(ids.ctypes.data, ids.dtype.itemsize, ids.size, bgrp.ctypes.data, bgrp.size, reverse)
 
+    L.setup_emul_candidates.restype = ctypes.c_int
+    L.setup_emul_candidates.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_int, ctypes.c_int]
     L.setup_emul_sell_roundtrip.restype = ctypes.c_int
     L.setup_emul_sell_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
     L.setup_emul_line_visits.restype = ctypes.c_ulonglong
@@ -60,6 +63,10 @@ def emul():
         ids = np.ascontiguousarray(ids)
         return L.setup_emul_line_visits(ids.ctypes.data, ids.dtype.itemsize, ids.size)
 
+    def candidates(a, b, reverse=0):
+        a, b = np.ascontiguousarray(a, dtype=np.int64), np.ascontiguousarray(b, dtype=np.int64)
+        return L.setup_emul_candidates(a.ctypes.data, a.size, b.ctypes.data, b.size, 8, reverse)
+
     def run(ids, reverse=0):
         ids = np.ascontiguousarray(ids)
         assert ids.dtype in (np.int64, np.int32)
@@ -67,6 +74,7 @@ def emul():
     run.split = split
     run.roundtrip = roundtrip
     run.visits = visits
+    run.candidates = candidates
     return run
 
 
@@ -167,3 +175,24 @@ def test_pair_ordering_reduces_line_visits(emul, monkeypatch):
     pairs_only = emul.visits(ids)
     monkeypatch.setenv("EXAGS_SELL_PAIRS", "2")
     assert emul.visits(ids) < pairs_only < 0.92 * plain
+
+
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_candidate_filters_never_drop_a_shared_label(emul, reverse):
+    """The device passes that pick, with np > 1, the labels another rank may hold
+    (setup_pipeline.h; the filters in front of shared_ids, src/gs.upc:190-244):
+    two label sets stand in for two ranks.  A label both hold must be a candidate,
+    the candidate rows must be the groups' (|label|, primary) in group order, and the
+    group lookup of the exchange plan's primaries must find every primary again."""
+    rng = np.random.default_rng(5)
+    slabs = [semmesh.box_ids(4, 3, 2, 3, ez0=2 * r, Ez_global=4) for r in range(2)]
+    assert emul.candidates(slabs[0], slabs[1], reverse) == 0
+    assert emul.candidates(slabs[1], slabs[0], reverse) == 0
+    for seed in range(6):
+        a = cases.random_ids(900 + 50 * seed, 300, 40 + seed)
+        b = cases.random_ids(700, 300, 80 + seed)
+        assert emul.candidates(a, b, reverse) == 0, seed
+    big = (rng.choice(2**20, size=500, replace=False).astype(np.int64) << 38) + 7     # widely spaced labels
+    assert emul.candidates(big[:300], big[200:], reverse) == 0
+    assert emul.candidates(np.arange(1, 100), np.arange(1000, 1100), reverse) == 0    # nothing shared
+    assert emul.candidates(np.zeros(0, np.int64), np.arange(1, 10), reverse) == 0

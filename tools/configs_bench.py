@@ -92,7 +92,11 @@ def run(name, mode, vn, dom, op, handle, transpose=0, weighted=False, secs=None)
     else:
         u = torch.ones(n * vn, dtype=dt, device="cuda")
     w = torch.full((n,), 0.5, dtype=dt, device="cuda") if weighted else None
-    if weighted:
+    if weighted and mode == X.mode_vec:
+        call = lambda: X.gs_weighted_vec(u, vn, w, dom, op, handle, stream)
+    elif weighted and mode == X.mode_many:
+        call = lambda: X.gs_weighted_many(u, vn, w, dom, op, handle, stream)
+    elif weighted:
         call = lambda: X.gs_weighted(u, w, dom, op, handle, stream)
     else:
         call = lambda: X.gs_async(u, mode, vn, dom, op, transpose, handle, stream)
@@ -149,6 +153,9 @@ run("gs_many(3,add,double)", X.mode_many, 3, X.gs_double, X.gs_add, g)
 run("gs_many(3,add,float)", X.mode_many, 3, X.gs_float, X.gs_add, g)
 run("gs_weighted(add,double)", X.mode_plain, 1, X.gs_double, X.gs_add, g, weighted=True)
 run("gs_weighted(add,float)", X.mode_plain, 1, X.gs_float, X.gs_add, g, weighted=True)
+run("gs_weighted_vec(3,add,double)", X.mode_vec, 3, X.gs_double, X.gs_add, g, weighted=True)
+run("gs_weighted_many(3,add,double)", X.mode_many, 3, X.gs_double, X.gs_add, g, weighted=True)
+run("gs_weighted_many(3,add,float)", X.mode_many, 3, X.gs_float, X.gs_add, g, weighted=True)
 # comm_dot on two device vectors of n doubles: 16 B per element, HBM-bound
 if not args.only or "comm_dot" in args.only:
     va, vb = torch.ones(n, dtype=torch.float64, device="cuda"), torch.full((n,), 0.5, dtype=torch.float64, device="cuda")
