@@ -1,23 +1,22 @@
 #!/bin/bash
 # tools/round_capture.sh TAG -- the standard evidence of one round in ONE gpurun call (1 GPU):
-#   gpurun --timeout 900 -- 'bash tools/round_capture.sh r2a'
-# 1. pytest -m gpu            -> gpurun_out/pytest_TAG.txt
-# 2. bench.py (default flags) -> gpurun_out/bench_TAG.json        (never under a profiler)
-# 3. the other configs        -> gpurun_out/configs_TAG.txt, weighted_TAG.txt
-# 4. ncu launch list of the bench command (only after 2 exited 0) -> launches_TAG.csv
-# 5. one `ncu --set full` capture of the hot kernel               -> prof_TAG.ncu-rep
-# Read the .ncu-rep on the CPU box with tools/ncu_summary.py and copy what is to be judged to profiles/.
-TAG=${1:-rX}
-O=gpurun_out
+#   gpurun --timeout 1500 -- 'bash tools/round_capture.sh r2i'
+# 1. pytest -m gpu, smoke()   -> gpurun_out/TAG_pytest.txt, TAG_smoke.txt
+# 2. bench.py (default flags) and its reference arm -> TAG_bench.json, TAG_bench_ref.json (never under a profiler)
+# 3. every other configuration -> TAG_configs.txt (tools/configs_bench.py); layout knobs -> TAG_knobs.txt
+# 4. one ncu --set full launch of every kernel on that list -> TAG_configs.ncu-rep (read here with
+#    tools/ncu_summary.py), and the launch list of the bench command -> TAG_launches.csv
+# Copy what is to be judged to profiles/.
+T=${1:-rX}; O=gpurun_out
 mkdir -p $O
-python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.txt 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_$TAG.txt
-python bench.py --steps 20 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; rc=$?; echo "bench rc=$rc"; cat $O/bench_$TAG.json
-timeout 300 python tools/configs_bench.py > $O/configs_$TAG.txt 2>&1; cat $O/configs_$TAG.txt
-timeout 120 python tools/weighted_bench.py > $O/weighted_$TAG.txt 2>&1; cat $O/weighted_$TAG.txt
-if [ $rc = 0 ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_${TAG}_a.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:k_fused_sell -s 3 -c 1 -o $O/prof_$TAG -f \
-      python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_${TAG}_b.log 2>&1
-  tail -2 $O/ncu_${TAG}_b.log
+python -m pytest tests -m gpu -q > $O/${T}_pytest.txt 2>&1; echo "pytest rc=$?"; tail -6 $O/${T}_pytest.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.txt 2>&1; echo "smoke rc=$?"; tail -2 $O/${T}_smoke.txt
+python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err; rc=$?; echo "bench rc=$rc"; cut -c1-600 $O/${T}_bench.json; tail -3 $O/${T}_bench.err
+python bench.py --impl reference --steps 20 --warmup 3 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err; echo "ref rc=$?"; cut -c1-400 $O/${T}_bench_ref.json
+timeout 600 python tools/configs_bench.py > $O/${T}_configs.txt 2>&1; echo "configs rc=$?"; cat $O/${T}_configs.txt
+if [ "$2" = "ncu" ] && [ $rc = 0 ]; then
+  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o $O/${T}_configs \
+      python tools/configs_bench.py --ncu > $O/${T}_ncu.log 2>&1; echo "ncu rc=$?"; tail -2 $O/${T}_ncu.log
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu > $O/${T}_ncu_launches.log 2>&1; echo "launch list rc=$?"
 fi
