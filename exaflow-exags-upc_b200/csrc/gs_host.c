@@ -912,13 +912,12 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   in.off = xnew(u32, ng + 1);
   in.idx = xnew(u32, ni ? ni : 1);
   if (any_flag) in.nunf = xnew(u32, ng ? ng : 1);
-  u32 *fs = xnew(u32, nfs ? nfs : 1);
   u32 *bgoff = xnew(u32, (size_t)nb + 1), *bgidx = xnew(u32, bni ? bni : 1), *bnunf = xnew(u32, nb ? nb : 1);
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthr)
 #endif
   for (int c = 0; c < NCH; ++c) {
-    u32 b = (u32)cb[c]; size_t og = cg[c], oi = ci[c], of = cf[c], ob = cbi[c];
+    u32 b = (u32)cb[c]; size_t og = cg[c], oi = ci[c], ob = cbi[c];
     for (size_t gi = GLO(c); gi < GLO(c + 1); ++gi) {
       u32 a = t->gstart[gi], e = t->gstart[gi + 1], unf = e - a;
       if (any_flag) { unf = 0; for (u32 j = a; j < e && !t->flag[j]; ++j) ++unf; }
@@ -934,7 +933,6 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
         memcpy(in.idx + oi, t->idx + a, (size_t)(e - a) * sizeof(u32));
         oi += e - a; ++og;
       }
-      if (e - a < 2 && t->flag[a]) fs[of++] = t->idx[a];
     }
   }
 #undef GLO
@@ -1013,7 +1011,7 @@ static void split_groups(struct gs_data *g, const struct xg_topo *t)
   }
   g->handle_bytes += ((size_t)ng + 1 + ni - nfs + nb + 1 + bni + nb) * sizeof(u32);   /* ng, ni count the flagged singles too */
   xg_sell_free(&sell);
-  xg_hmap_free(&in); free(fs); free(bgoff); free(bgidx); free(bnunf);
+  xg_hmap_free(&in); free(bgoff); free(bgidx); free(bnunf);
 }
 
 /* time the exchange step alone, the way dry_run_time does
