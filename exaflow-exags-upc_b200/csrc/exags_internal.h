@@ -104,9 +104,13 @@ void xg_hmap_free(struct xg_hmap *m);
 #ifndef XG_SELL_WB
 #define XG_SELL_WB   8     /* blocks per window (a multiple of XG_SELL_CW)            */
 #endif
+#ifndef XG_SELL_CW
 #define XG_SELL_CW   8     /* blocks per CTA of the sliced kernels = warps per CTA.
                               Measured: a window split over two CTAs loses the L1
                               reuse the chain order creates (profiles/r1_sweep10) */
+#endif
+/* resident CTAs per SM are quoted for 8-warp CTAs; scaled for other CTA sizes */
+#define XG_MINB(m) (((m) * 8 + XG_SELL_CW - 1) / XG_SELL_CW)
 struct xg_sell {
   u32  nblock;        /* multiple of XG_SELL_WB                              */
   unsigned char *mask;/* [nblock*32] start mask of each lane                 */

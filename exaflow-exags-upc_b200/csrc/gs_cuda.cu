@@ -366,7 +366,7 @@ __device__ __forceinline__ void sell_lane(const Fld<T, MODE> &f, const uint4 a, 
 }
 
 template <typename T, int OP, int MODE, int KU, int MINB, bool GONLY = false, bool FLG = false, bool ONE = false>
-__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_CW, XG_MINB(MINB))
 k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
 {
   const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
@@ -384,7 +384,7 @@ k_fused_sell(xcu_sell m, Fld<T, MODE> f, int transpose)
 // component of a vector field), against a separate pass over the whole field
 // (read u, read w, write u).
 template <typename T, int OP, int MODE, int KU, int MINB, bool FLG, bool ONE, int WL = 1>
-__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_CW, XG_MINB(MINB))
 k_fused_sell_w(xcu_sell m, Fld<T, MODE> f, const T *__restrict__ wgt, int transpose)
 {
   const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
@@ -483,7 +483,7 @@ __device__ __forceinline__ void vec3_lane(T *__restrict__ u, const uint4 a, cons
 }
 
 template <typename T, int OP, int MINB>
-__global__ void __launch_bounds__(32 * XG_SELL_CW, MINB)
+__global__ void __launch_bounds__(32 * XG_SELL_CW, XG_MINB(MINB))
 k_fused_sell_vec3(xcu_sell m, T *__restrict__ u)
 {
   const u32 c = blockIdx.x * (u32)XG_SELL_CW + (threadIdx.x >> 5);
@@ -602,9 +602,6 @@ k_bnd_pack(xcu_bnd bd, Fld<T, MODE> f, int transpose, T *__restrict__ sendbuf,
 // and slot s only has to carry u[sprim[s]] -- scatter_to_buf of
 // src/gs.upc:490 read the other way round.  Consecutive threads fill
 // consecutive slots, so the stores into a neighbour's mailbox are contiguous.
-#ifndef XG_PACK_UNROLL
-#define XG_PACK_UNROLL 4      // slots per thread and pass: that many independent field loads in flight
-#endif
 template <typename T, int MODE, bool PUSH>
 __global__ void __launch_bounds__(256)
 k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__restrict__ sendbuf,
@@ -612,43 +609,23 @@ k_pack_slots(const u32 *__restrict__ sprim, u32 nslots, Fld<T, MODE> f, T *__res
 {
   const u32 epoch = PUSH ? push_epoch(pp) : 0u;
   const unsigned long long *pbase = PUSH ? pp.base + (size_t)(epoch & 1u) * pp.par_stride : nullptr;
-  const u32 stride = gridDim.x * 256u;
-  for (u32 s0 = blockIdx.x * 256u + threadIdx.x; s0 < nslots; s0 += XG_PACK_UNROLL * stride) {
-    // gather first: the loads of the slots of one pass do not depend on each other
-    u32 prim[XG_PACK_UNROLL];
-    T val[XG_PACK_UNROLL];
-#pragma unroll
-    for (int q = 0; q < XG_PACK_UNROLL; ++q) {
-      const u32 s = s0 + (u32)q * stride;
-      prim[q] = s < nslots ? __ldg(sprim + s) : 0u;
+  for (u32 s = blockIdx.x * 256u + threadIdx.x; s < nslots; s += gridDim.x * 256u) {
+    const u32 prim = __ldg(sprim + s);
+    T *dst = sendbuf;
+    u32 slot = s;
+    if (PUSH) {
+      u32 lo = 0, hi = pp.nnb;                    // neighbour whose slot range holds s
+      while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (__ldg(pp.start + mid) <= s) lo = mid; else hi = mid; }
+      dst = reinterpret_cast<T *>(__ldg(pbase + lo));
+      slot = s + __ldg(pp.delta + lo);
     }
-    if (f.vn == 1) {
-#pragma unroll
-      for (int q = 0; q < XG_PACK_UNROLL; ++q) if (s0 + (u32)q * stride < nslots) val[q] = *f.at(prim[q], 0);
-    }
-#pragma unroll
-    for (int q = 0; q < XG_PACK_UNROLL; ++q) {
-      const u32 s = s0 + (u32)q * stride;
-      if (s >= nslots) break;
-      T *dst = sendbuf;
-      u32 slot = s;
-      if (PUSH) {
-        u32 lo = 0, hi = pp.nnb;                  // neighbour whose slot range holds s
-        while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (__ldg(pp.start + mid) <= s) lo = mid; else hi = mid; }
-        dst = reinterpret_cast<T *>(__ldg(pbase + lo));
-        slot = s + __ldg(pp.delta + lo);
-      }
-      if (f.vn == 1) dst[(size_t)slot * bufvn + f.k0] = val[q];
-      else for (unsigned k = 0; k < f.vn; ++k) dst[(size_t)slot * bufvn + f.k0 + k] = *f.at(prim[q], k);
-    }
+    for (unsigned k = 0; k < f.vn; ++k)
+      dst[(size_t)slot * bufvn + f.k0 + k] = *f.at(prim, k);
   }
   if (PUSH && pp.nsig) {
-    // The CTA's peer stores must be out before its arrival is counted.  The
-    // barrier orders every thread's stores before thread 0's fence, and a fence
-    // is cumulative: one system-scope fence per CTA instead of one per thread.
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence_system();
       const unsigned done = atomicAdd(pp.counter, 1u);
       if (done == gridDim.x - 1u) {
         *pp.counter = 0u;

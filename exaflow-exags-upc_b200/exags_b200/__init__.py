@@ -20,7 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libexags.so")
+LIB_PATH = os.environ.get("EXAGS_LIB_PATH") or os.path.join(_HERE, "libexags.so")   # override: variant builds for A/B runs
 
 # gs_dom / gs_op / gs_method values (src/gs_defs.h:59-79, src/gs.h:127)
 gs_double, gs_float, gs_int, gs_long, gs_long_long = 0, 1, 2, 3, 4

@@ -18,7 +18,15 @@ extern "C" {
    `stream` is a cudaStream_t; the work is ordered after what is already in
    that stream and later work in that stream is ordered after it.
    mode: 0 plain (u = T*), 1 vec (u = T[n][vn]), 2 many (u = host table of vn
-   device pointers).                                                        */
+   device pointers).
+   CUDA graphs: the call makes no allocation and no host synchronisation, so it
+   can be captured and replayed -- with several ranks too when the halo exchange
+   is the push transport (the number of the exchange is device state, see
+   DESIGN.md 5).  Capture after one ordinary call with the same handle and the
+   largest vn * sizeof(T) the graph will use: that call sizes the handle's
+   mailbox, and a later call that needs a larger one re-creates it, which would
+   leave an older graph pointing at freed memory.  Every rank must replay the
+   same number of exchanges, as with the plain calls.                        */
 void exags_gs_async(void *u, int mode, unsigned vn, int dom, int op,
                     unsigned transpose, struct gs_data *gsh, void *stream);
 
