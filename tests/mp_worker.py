@@ -90,6 +90,9 @@ def main():
     if gpu:
         ndev = torch.cuda.device_count()
         X.lib().exags_set_device(rank % ndev)
+    if rank == 0 and os.environ.get("TEST_RANK0_DELAY_S"):
+        import time                       # the other ranks reach the library's rendezvous first
+        time.sleep(float(os.environ["TEST_RANK0_DELAY_S"]))
     ids = make_ids(case, np_, rank)
     if unique and case.startswith("fuzz"):
         ids = np.abs(ids)     # unique on pre-flagged labels is the reference quirk of DESIGN.md 2, not compared

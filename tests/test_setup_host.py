@@ -121,3 +121,41 @@ def test_dead_rank_ends_the_wait(built):
     assert codes[2] == 7
     assert codes[0] == 1 and codes[1] == 1, (codes, outs)
     assert "is gone while rank" in outs[0] and "ERROR (proc" in outs[0]
+
+
+def test_stale_rendezvous_segment_is_replaced(built):
+    """A rendezvous segment left in /dev/shm by a killed run with the same job key
+    (only atexit unlinks it) carries a dead owner: late ranks must not attach to
+    it, rank 0 replaces it, and the job runs (comm.c rendezvous)."""
+    import ctypes
+    import mp_launch
+    import uuid
+    key = "stale" + uuid.uuid4().hex[:10]
+    path = f"/dev/shm/exags-{key}-ctl"
+    # what a dead run leaves behind: right size, magic set, every rank "attached", owner pid gone
+    XW_MAXNP, XW_SMALL = 64, 4096
+    size = 4 * 5 + 4 * XW_MAXNP + 8 + 8 * XW_MAXNP + XW_MAXNP * XW_SMALL + 64
+    blob = bytearray(size)
+    blob[0:4] = (0x45584147).to_bytes(4, "little")      # magic
+    blob[4:8] = (2).to_bytes(4, "little")               # np
+    blob[8:12] = (2).to_bytes(4, "little")              # attached
+    blob[20:24] = (2 ** 22 - 3).to_bytes(4, "little")   # pid[0]: no such process
+    blob[280:288] = (12345).to_bytes(8, "little")       # owner_start (after pid[64], 8-byte aligned)
+    with open(path, "wb") as f:
+        f.write(blob)
+    try:
+        port = 20000 + (uuid.uuid4().int % 30000)
+        procs = []
+        import os, subprocess, sys
+        for r in range(2):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                       MASTER_PORT=str(port), EXAGS_JOB_KEY=key, OMP_NUM_THREADS="2",
+                       TEST_RANK0_DELAY_S="2")      # rank 1 meets the stale segment before rank 0 replaces it
+            procs.append(subprocess.Popen([sys.executable, os.path.join(mp_launch.HERE, "mp_worker.py"),
+                                           "fixture", "setup", "0", "1"], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=180)[0] for p in procs]
+        assert [p.returncode for p in procs] == [0, 0], outs
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
