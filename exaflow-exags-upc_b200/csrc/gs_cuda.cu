@@ -2,6 +2,12 @@
 // host C code calls them through.
 //
 // What the kernels replace (reference paths relative to /root/reference):
+//   k_fused_sell   the same fused pass over the sliced-ELL layout (the hot
+//                  kernel: one warp per 1 KB block of member indices, one CTA
+//                  per window; variants: KU = 3 components per pass, vec3
+//                  tuples, FLG flag masks, GONLY gather only, WGT weights)
+//   k_pack_slots / k_push_wait   pw_exec_sends / pw_exec_recvs as peer stores
+//                  over NVLink and a flag wait (src/gs.upc:409-468)
 //   k_fused        gather_T_OP + init_T + scatter_T run back to back by
 //                  gs_aux (src/gs.upc:1181-1184, src/gs_local.c:60-97) --
 //                  one pass over a CSR map instead of two passes over a

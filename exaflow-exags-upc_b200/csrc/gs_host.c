@@ -5,13 +5,18 @@
  * runs four serial passes per call: local gather, init, remote exec, local
  * scatter.  Here one call is
  *
- *   np == 1:  one fused kernel over the CSR map in HBM (+ a tiny init kernel
- *             when flagged singletons exist);
+ *   np == 1:  one fused kernel over the sliced-ELL map in HBM (flagged
+ *             singles are one-member groups of that map: no init pass);
  *   np  > 1:  groups are split at setup into interior (no remote sharer) and
- *             boundary.  Boundary work -- gather+pack, NCCL grouped
- *             send/recv over NVLink, unpack+scatter -- runs on a
- *             high-priority stream while the fused interior kernel runs on
- *             the caller's stream; an event joins the two.
+ *             boundary.  Boundary work -- reduce, pack with peer stores into the
+ *             neighbours' mailboxes over NVLink (or NCCL grouped send/recv, or
+ *             CUDA-IPC pulls between ranks sharing a GPU), flag wait,
+ *             unpack+scatter -- runs on a high-priority stream while the fused
+ *             interior kernel runs on the caller's stream; an event joins the
+ *             two.  The number of the exchange is device state, so the same
+ *             launches can be replayed from a CUDA graph.
+ *   host u:   chunked H2D / window waves / D2H pipeline; pageable arrays pass
+ *             through pinned bounce rings filled by the host cores.
  *
  * There is no CPU execution path: without a CUDA device gs() fails loudly.
  */
@@ -24,7 +29,6 @@
 
 struct dev_csr { struct xcu_csr c; u32 *off, *idx, *nunf; };
 #define XG_RING 3                     /* slots of each pinned bounce ring (pageable host arrays) */
-
 
 struct gs_data {
   comm_ptr comm;
