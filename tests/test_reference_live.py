@@ -21,7 +21,9 @@ def test_oracle_matches_reference(O, np_, unique, method, seed):
     ids = [cases.random_ids(260 + 13 * r, 70, 1000 * seed + r, p_flag=0.0 if unique else 0.25) for r in range(np_)]
     combos = [(1, 8, 0, 0, 0)] + [(m, vn, d, o, t) for (m, vn), (d, o), t in
                                   itertools.product(((0, 1), (1, 2), (2, 2)), ((0, 0), (2, 3), (3, 2), (1, 1)), (0, 1))]
-    data = [[cases.values(ids[r].size * (1 if m == 0 else vn), DT[d], cases.OPS[o], 31 * k + r) for r in range(np_)]
+    # gs_bpr (src/gs_defs.h:37-42; xxt.upc:623 issues it on sint), every domain the reference instantiates it for
+    combos += [(0, 1, 2, 4, 0), (1, 2, 3, 4, 1), (2, 2, 0, 4, 0), (0, 1, 1, 4, 1)]
+    data = [[cases.values(ids[r].size * (1 if m == 0 else vn), DT[d], cases.OPS_BPR[o], 31 * k + r) for r in range(np_)]
             for k, (m, vn, d, o, t) in enumerate(combos)]
     mine = [[a.copy() for a in row] for row in data]
     maps, _ = ref.run(ids, combos, data, unique=unique, method=method, want_maps=True)
