@@ -827,11 +827,22 @@ k_dot_partial(const double *__restrict__ v, const double *__restrict__ w, size_t
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
 
-__global__ void k_dot_final(const double *__restrict__ part, unsigned nparts, double *__restrict__ out)
+// one CTA folds the partials: strided sums per thread, then the same tree as
+// above -- a fixed order again.  (A single thread adding the 1184 partials one
+// after the other took 51 us, profiles/r2_ncu_all_kernels_h_table.txt.)
+__global__ void __launch_bounds__(DOT_THREADS)
+k_dot_final(const double *__restrict__ part, unsigned nparts, double *__restrict__ out)
 {
-  double s = 0;
-  for (unsigned i = 0; i < nparts; ++i) s += part[i];
-  *out = s;
+  __shared__ double sh[DOT_THREADS];
+  double acc = 0;
+  for (unsigned i = threadIdx.x; i < nparts; i += DOT_THREADS) acc += part[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (unsigned s = DOT_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -1214,7 +1225,7 @@ void xcu_dot(void *stream, const double *v, const double *w, size_t n, double *s
   if (nb == 0) nb = 1;
   k_dot_partial<<<nb, DOT_THREADS, 0, st>>>(v, w, n, scratch);
   LAUNCHED();
-  k_dot_final<<<1, 1, 0, st>>>(scratch, nb, out);
+  k_dot_final<<<1, DOT_THREADS, 0, st>>>(scratch, nb, out);
   LAUNCHED();
 }
 
