@@ -2,8 +2,8 @@
     for s in $(seq 100 139); do timeout -s KILL 25 python oracle/ref_fuzz.py $s | tail -1; done
 TEST INFRASTRUCTURE ONLY.  Run each job under `timeout`: the reference's pairwise exchange can
 deadlock under the shim when ranks need different mailbox sizes.  The seed picks
-np in {1,2,4,8}, the method, unique, label density, zeros and flags; 31 cases per job cover
-plain / vec / many, five dom x op pairs and both transposes.  Round 1: seeds 100-139 gave 38
+np in {1,2,4,8}, the method, unique, label density, zeros and flags; 37 cases per job cover
+plain / vec / many, six dom x op pairs (incl. gs_bpr) and both transposes.  Round 1: seeds 100-139 gave 38
 identical jobs, one reference failure (126) and one reference hang (131)."""
 import sys, itertools
 import os; _R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[os.path.join(_R,'exaflow-exags-upc_b200'),os.path.join(_R,'oracle'),os.path.join(_R,'tests')]
@@ -14,8 +14,8 @@ rng=np.random.default_rng(seed)
 np_=int(rng.choice([1,2,4,8])); unique=int(rng.random()<0.3); method=int(rng.choice([1,1,3]))
 nl=int(rng.integers(3,200))
 ids=[cases.random_ids(int(rng.integers(0,400))+5, nl, 1000*seed+r, p_zero=float(rng.choice([0,0.2])), p_flag=0.0 if unique else float(rng.choice([0,0.25,0.8]))) for r in range(np_)]
-combos=[(1,8,0,0,0)]+[(m,vn,d,o,t) for (m,vn),(d,o),t in itertools.product(((0,1),(1,3),(2,2)),((0,0),(2,3),(3,2),(1,1),(0,2)),(0,1))]
-data=[[cases.values(ids[r].size*(1 if m==0 else vn), DT[d], cases.OPS[o], 31*k+r) for r in range(np_)] for k,(m,vn,d,o,t) in enumerate(combos)]
+combos=[(1,8,0,0,0)]+[(m,vn,d,o,t) for (m,vn),(d,o),t in itertools.product(((0,1),(1,3),(2,2)),((0,0),(2,3),(3,2),(1,1),(0,2),(2,4)),(0,1))]      # the last pair: gs_bpr on int
+data=[[cases.values(ids[r].size*(1 if m==0 else vn), DT[d], cases.OPS_BPR[o], 31*k+r) for r in range(np_)] for k,(m,vn,d,o,t) in enumerate(combos)]
 mine=[[a.copy() for a in row] for row in data]
 maps,_=ref.run(ids,combos,data,unique=unique,method=method,want_maps=True)
 orc=O.Oracle(ids,unique=unique,method=O.METHOD_ALLREDUCE if method==3 else O.METHOD_PAIRWISE)
